@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py -- the headline measurement of BASELINE.json: DD^dagger site-updates/s on the
+8192x8192 lattice (beta=2, m0=0; configs[3]), with CG solves/s (configs[1], 256^2) and HMC
+trajectories/s (configs[2], 1024^2) reported beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]             the B200 path (libschwinger_b200.so)
+    python bench.py --impl reference [...]                           the reference's CPU code on host cores
+
+One "step" is one D D^dagger application over the whole lattice (two Wilson-stencil launches).
+`value` is site-updates/s with every field resident in HBM; `e2e` is the same unit measured
+through the reference-facing conjugate_gradient() call of the C ABI with pinned HOST buffers
+(U and phi copied in, x copied out inside the timed region): DD^dagger applications the solve
+performed x sites / wall time.  N > 1 splits the same 8192^2 lattice over ranks_x = N GPUs
+(strong scaling, the decomposition configs[3] names); launch with torchrun as the driver does.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "DD^dagger site-updates/s"
+UNIT = "site-updates/s"
+BYTES_PER_STENCIL_SITE = 96      # read psi 32 + read U 32 + write 32  
+BYTES_PER_DD_SITE = 192
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        threading.Thread(target=self._read, daemon=True).start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synthetic_links(V, seed):
+    """hot-start gauge field: U = exp(i theta), theta ~ U[0, 2 pi)  (gauge_conf.cpp:23-36)"""
+    rng = np.random.default_rng(seed)
+    out = np.empty((2, V), np.complex128)
+    for mu in range(2):
+        th = rng.random(V) * (2.0 * np.pi)
+        out[mu].real = np.cos(th)
+        out[mu].imag = np.sin(th)
+    return out
+
+
+def synthetic_spinor(V, seed):
+    """Gaussian pseudofermion source: re, im ~ N(0, 1/sqrt 2)  (hmc.cpp:19-28)"""
+    rng = np.random.default_rng(seed)
+    out = np.empty((2, V), np.complex128)
+    v = out.view(np.float64)
+    v[...] = rng.standard_normal(v.shape) * np.sqrt(0.5)
+    return out
+
+
+def pinned_like(a):
+    """numpy view of pinned host memory holding a copy of `a` (torch is plumbing only)."""
+    import torch
+    t = torch.empty(a.shape, dtype=torch.complex128 if a.dtype == np.complex128 else torch.float64, pin_memory=True)
+    n = t.numpy()
+    n[...] = a
+    return t, n
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU code (oracle/_ref) on the box's host cores
+# ---------------------------------------------------------------------------------------------------
+def reference_sample(args, n_threads=None):
+    """DD^dagger site-updates/s of the UNMODIFIED reference, forked over the host cores through the
+    mini-MPI shim, on a bounded sample: a 2048x2048 lattice (1/16 of the 8192^2 sites; the per-site
+    work and access pattern are size-independent once the fields exceed the CPU caches)."""
+    from oracle import ref as refmod
+    nx = nt = args.ref_lattice
+    cores = os.cpu_count() or 1
+    if n_threads is None:
+        n_threads = cores
+    rx = 1
+    while rx * 2 <= min(n_threads, 64) and nx % (rx * 2) == 0 and nx // (rx * 2) >= 2:
+        rx *= 2
+    kind = "reference"
+    if not refmod.available(nx, nt):
+        return None, None, None, None
+    R = refmod.Ref(nx, nt)
+    U = synthetic_links(nx * nt, 1)
+    phi = synthetic_spinor(nx * nt, 2)
+    return R, U, phi, (rx, kind)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    R, U, phi, info = reference_sample(args)
+    if R is None:
+        # the reference did not compile here: time the C port (1 core)
+        from oracle.port import Port
+        nx = nt = args.ref_lattice
+        P = Port(nx, nt)
+        U, phi = synthetic_links(nx * nt, 1), synthetic_spinor(nx * nt, 2)
+        times = []
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            P.DDdag(U, phi, 0.0)
+            times.append(time.perf_counter() - t0)
+        per = float(np.mean(times[args.warmup:]))
+        rx, kind, cores = 1, "port", 1
+    else:
+        rx, kind = info
+        cores = rx
+        reps = 2
+        times = []
+        for i in range(args.warmup + args.steps):
+            sec, count, _ = R.timed("dd", U, phi, 0.0, rx, 1, reps=reps)
+            times.append(sec / reps)
+        per = float(np.mean(times[args.warmup:]))
+    V = args.ref_lattice ** 2
+    val = V / per
+    sample = (f"{args.ref_lattice}x{args.ref_lattice} lattice (1/{(args.lattice // args.ref_lattice) ** 2} of the "
+              f"{args.lattice}^2 workload), D_D_dagger_phi of the reference over {cores} forked ranks "
+              f"(ranks_x={rx}, ranks_t=1), {args.steps} timed steps")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": per * 1e3 * (args.lattice / args.ref_lattice) ** 2,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"DD^dagger on {args.lattice}x{args.lattice}, beta=2, m0=0 (BASELINE configs[3])",
+                   "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "host_cores": os.cpu_count(),
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def cpu_baseline(args):
+    """rank 0, N=1 only: a bounded sample of the same workload on the host cores."""
+    t_start = time.time()
+    R, U, phi, info = reference_sample(args)
+    if R is None:
+        from oracle.port import Port
+        n = 1024
+        P = Port(n, n)
+        U, phi = synthetic_links(n * n, 1), synthetic_spinor(n * n, 2)
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            P.DDdag(U, phi, 0.0)
+        per = (time.perf_counter() - t0) / reps
+        return {"value": n * n / per, "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": f"{reps} x DD^dagger on a {n}x{n} lattice with the C port, 1 core"}
+    rx, kind = info
+    n = args.ref_lattice
+    best = None
+    reps, rounds = 2, 0
+    while time.time() - t_start < 20 and rounds < 6:
+        sec, count, _ = R.timed("dd", U, phi, 0.0, rx, 1, reps=reps)
+        per = sec / reps
+        best = per if best is None else min(best, per)
+        rounds += 1
+    return {"value": n * n / best, "unit": UNIT, "cores": rx, "kind": kind,
+            "sample": f"best of {rounds} x {reps} D_D_dagger_phi on a {n}x{n} lattice (1/{(args.lattice // n) ** 2} of the "
+                      f"workload) by the unmodified reference over {rx} forked ranks (mini-MPI shim), "
+                      f"{os.cpu_count()} host cores present"}
+
+
+# ---------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import schwingermodel_b200 as sb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+        args.gpus = world
+    N = args.gpus
+    torch.cuda.set_device(local_rank)
+    nccl_id = None
+    if N > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(sb.Lattice.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.cpu().numpy().tobytes())
+
+    def barrier():
+        if N > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if N == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    L = args.lattice
+    m0, beta = 0.0, 2.0
+    lat = sb.Lattice(L, L, device=local_rank, ranks_x=N, ranks_t=1, rank=rank, nccl_id=nccl_id)
+    V = lat.V
+    U_h = synthetic_links(V, 1000 + rank)
+    phi_h = synthetic_spinor(V, 2000 + rank)
+    dU, dphi, dout = lat.new_field(True, U_h), lat.new_field(True, phi_h), lat.new_field(True)
+
+    # ---- device-resident DD^dagger: W warm-up steps, then exactly K timed steps --------------------
+    lat.dev_DDdag_loop(dU, dphi, dout, m0, max(args.warmup, 3))
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = lat.launch_count()
+    barrier()
+    ms = lat.dev_DDdag_loop(dU, dphi, dout, m0, args.steps)     # CUDA events on the launching stream
+    barrier()
+    launches = lat.launch_count() - l0
+    ms = max_over_ranks(ms)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms / args.steps
+    value = (L * L) / (ms_per_step * 1e-3)
+
+    peak, peak_src = measured_peaks()
+    stencil_launches = 2 * args.steps
+    avg_launch_ms = ms / stencil_launches
+    achieved = BYTES_PER_STENCIL_SITE * V / (avg_launch_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get("k_wilson_bytes_per_launch")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel": "k_wilson (Wilson stencil D / D^dagger)",
+                "algorithmic_bytes_per_launch": BYTES_PER_STENCIL_SITE * V, "avg_launch_ms": avg_launch_ms}
+
+    # ---- e2e: the reference-facing conjugate_gradient() with pinned host buffers --------------------
+    keepU, U_p = pinned_like(U_h)
+    keepP, phi_p = pinned_like(phi_h)
+    keepX, x_p = pinned_like(phi_h)
+    lat.set_cg(1e-10, 10000)
+    e2e_steps = max(1, min(args.e2e_steps, args.steps))
+    if args.warmup > 0:
+        _cg_into(lat, U_p, phi_p, x_p, m0)      # one untimed solve
+    barrier()
+    t0 = time.perf_counter()
+    apps = 0
+    for _ in range(e2e_steps):
+        x, ok, its = _cg_into(lat, U_p, phi_p, x_p, m0)
+        apps += its + 2
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": apps * (L * L) / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": int(N * 2 * U_p.nbytes), "d2h_bytes_per_step": int(N * x_p.nbytes),
+           "call": "sm_conjugate_gradient (host buffers)", "solves": e2e_steps, "dd_applications": apps,
+           "cg_converged": int(ok), "seconds": e2e_s, "solves_per_s": e2e_steps / e2e_s}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"DD^dagger on {L}x{L}, beta=2, m0=0, hot-start links, Gaussian source "
+                               f"(BASELINE configs[3]); ranks_x={N}, ranks_t=1",
+                   "l2": "inputs larger than L2 (each field %.0f MiB per GPU)" % (V * 32 / 2 ** 20),
+                   "step": "one D D^dagger application over the whole lattice"},
+        "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "hbm_gbs_effective": BYTES_PER_DD_SITE * value / 1e9 / N,
+    }
+
+    # ---- the other two parts of BASELINE.json's metric (rank 0, single GPU) -------------------------
+    if N == 1 and not args.skip_extra:
+        line["extra"] = extra_metrics(sb, args)
+        line["cpu_baseline"] = cpu_baseline(args)
+    if rank == 0:
+        print(json.dumps(line))
+    lat.close()
+    if N > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def _cg_into(lat, U, phi, x, m0):
+    """sm_conjugate_gradient writing into a caller-owned (pinned) x."""
+    import ctypes as C
+
+    from schwingermodel_b200._abi import check, dp
+    ok, its = C.c_int(0), C.c_int(0)
+    p = lambda r: r.ctypes.data_as(dp)   # noqa: E731
+    check(lat.lib.sm_conjugate_gradient(lat.ctx, p(U[0]), p(U[1]), p(phi[0]), p(phi[1]), p(x[0]), p(x[1]), float(m0),
+                                        C.byref(ok), C.byref(its)))
+    return x, ok.value, its.value
+
+
+def extra_metrics(sb, args):
+    out = {}
+    # configs[1]: 256x256, beta=2, m0=0, one CG solve of (DD^dagger)^-1 on a hot-start field
+    lat = sb.Lattice(256, 256)
+    U, phi = synthetic_links(256 * 256, 1), synthetic_spinor(256 * 256, 2)
+    dU, dphi, dx = lat.new_field(True, U), lat.new_field(True, phi), lat.new_field(True)
+    for _ in range(3):
+        ok, its = lat.dev_cg(dU, dphi, dx, 0.0)
+    t = []
+    for _ in range(10):
+        ok, its = lat.dev_cg(dU, dphi, dx, 0.0)
+        t.append(lat.last_kernel_ms())
+    out["cg_256"] = {"solves_per_s": 1e3 / float(np.mean(t)), "iterations": its, "converged": ok,
+                     "ms_per_solve": float(np.mean(t)), "config": "256x256 hot start, m0=0, tol 1e-10 (configs[1])"}
+    lat.close()
+    # configs[2]: 1024x1024, beta=4, m0=-0.05, full HMC trajectories device-resident (MD=10, tau=1)
+    n = 1024
+    lat = sb.Lattice(n, n)
+    h = sb.HMC(lat, synthetic_links(n * n, 3), 10, 1.0, 0, 0, 0, 4.0, -0.05, seed=11)
+    h.HMC_Update()
+    t0 = time.perf_counter()
+    ntr = 3
+    for _ in range(ntr):
+        h.HMC_Update()
+    dt = time.perf_counter() - t0
+    out["hmc_1024"] = {"traj_per_s": ntr / dt, "dd_applications_per_traj": int(np.mean([x[2] for x in h.history[1:]])),
+                       "kernel_ms_per_traj": float(np.mean([x[4] for x in h.history[1:]])),
+                       "dH": [x[0] for x in h.history], "all_cg_converged": all(x[3] for x in h.history),
+                       "config": "1024x1024, beta=4, m0=-0.05, MD=10, tau=1, from a hot start (configs[2])"}
+    lat.close()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--lattice", type=int, default=8192)
+    ap.add_argument("--ref-lattice", type=int, default=2048)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--skip-extra", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

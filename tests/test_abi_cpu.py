@@ -1,0 +1,73 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol
+include/schwinger_b200.h declares, refuses to work without a GPU (no CPU fallback), and its
+host-only configuration-file routines are byte-exact against the reference's SaveConf output."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, load_golden
+
+import schwingermodel_b200 as sb
+from schwingermodel_b200 import _abi
+
+
+def test_library_is_built_and_exports_every_declared_symbol():
+    names = sb.declared_symbols()
+    assert len(names) >= 40 and len(set(names)) == len(names)
+    lib = sb.load()
+    for n in names:
+        assert hasattr(lib, n), f"libschwinger_b200.so lacks {n}"
+    # the Python binding types exactly the declared set
+    assert set(_abi._SIGS) | {"sm_last_error"} == set(names)
+    out = subprocess.run(["nm", "-D", "--defined-only", sb.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    assert set(names) <= exported
+
+
+def test_built_for_sm_100a_only():
+    out = subprocess.run(["cuobjdump", "-lelf", sb.LIB_PATH], capture_output=True, text=True).stdout
+    archs = {l.split(".")[-2] for l in out.splitlines() if "sm_" in l}
+    assert archs == {"sm_100a"}, out
+
+
+def test_no_gpu_no_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(sb.SchwingerError) as e:
+        sb.Lattice(8, 8)
+    assert e.value.code == _abi.SM_ERR_CUDA and "no CPU fallback" in str(e.value)
+
+
+def test_argument_errors_are_reported_not_thrown():
+    lib = sb.load()
+    ctx = _abi.ctx_p()
+    assert lib.sm_create(1, 8, 0, C.byref(ctx)) == _abi.SM_ERR_ARG
+    assert b"2x2" in lib.sm_last_error()
+    assert lib.sm_create(8, 8, 0, None) == _abi.SM_ERR_ARG
+    assert lib.sm_local_dims(None, None) == _abi.SM_ERR_ARG
+    assert lib.sm_create_dist(8, 8, 3, 1, 0, 0, b"x" * 128, C.byref(ctx)) == _abi.SM_ERR_ARG   # 8 % 3 != 0
+    assert b"divisible" in lib.sm_last_error()
+
+
+def test_config_file_bytes(tmp_path):
+    g = load_golden(8, 8)
+    f = tmp_path / "a.ctxt"
+    sb.SaveConf(g["U"], 8, 8, str(f))
+    want = open(os.path.join(GOLDEN, "ref_8x8.ctxt"), "rb").read()
+    assert f.read_bytes() == want and len(want) == 2 * 64 * 28
+    assert np.array_equal(sb.readBinary(8, 8, os.path.join(GOLDEN, "ref_8x8.ctxt")), g["U"])
+    with pytest.raises(sb.SchwingerError):
+        sb.readBinary(8, 8, str(tmp_path / "missing.ctxt"))
+
+
+def test_file_name_tags_and_jackknife():
+    s = np.load(os.path.join(GOLDEN, "ref_64x64_scalars.npz"))
+    assert [sb.format_tag(2.0), sb.format_tag(-0.18), sb.format_tag(0.0)] == [str(x) for x in s["strings"]]
+    from oracle.port import Port
+    rng = np.random.default_rng(0)
+    d = rng.normal(size=47)
+    assert abs(sb.jackknife_error(d, 20) - Port(2, 2).jackknife(d, 20)) < 1e-15

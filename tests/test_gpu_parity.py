@@ -1,0 +1,342 @@
+"""GPU parity: libschwinger_b200.so (through the C ABI, host-mirror class Lattice) against
+  (1) the golden vectors the UNMODIFIED reference produced (tests/golden/*.npz), and
+  (2) the C oracle (oracle/schwinger_oracle.c, itself pinned bit-exactly to the reference)
+on the same seeded inputs.  Tolerances are BASELINE.json's: tables bit-exact, one D / D^dagger
+application <= 1e-13 relative, CG same flag / iterations within +-1 / solution to the stated
+residual, dH <= 1e-8.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+CASES = [(8, 8), (16, 24), (32, 32)]
+TOL_D = 1e-13          # one stencil application, relative (north_star)
+TOL_X = 1e-9           # CG solution, relative
+TOL_DH = 1e-8          # per trajectory (north_star)
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import schwingermodel_b200 as m
+    return m
+
+
+@pytest.fixture(scope="module", params=CASES, ids=lambda c: f"{c[0]}x{c[1]}")
+def case(request, sb):
+    nx, nt = request.param
+    lat = sb.Lattice(nx, nt)
+    yield lat, load_golden(nx, nt)
+    lat.close()
+
+
+def test_tables_bit_exact(case):
+    lat, g = case
+    t = lat.periodic_boundary()
+    for k, v in t.items():
+        assert np.array_equal(v, g["tab_" + k]), k
+    t22 = lat.periodic_boundary(2, 2, 3)
+    flat = np.concatenate([v.view(np.float64).ravel() if v.dtype == np.complex128 else v.astype(np.float64)
+                           for v in t22.values()])
+    assert np.array_equal(flat, g["tab22_rank3"])
+
+
+def test_tables_every_rank_vs_oracle(sb):
+    from oracle.port import Port
+    lat, P = sb.Lattice(16, 24), Port(16, 24)
+    for rx, rt in [(2, 1), (1, 2), (2, 2), (4, 3), (1, 8)]:
+        for rank in range(rx * rt):
+            a, b = lat.periodic_boundary(rx, rt, rank), P.tables(rx, rt, rank)
+            for k in a:
+                assert np.array_equal(a[k], b[k]), (rx, rt, rank, k)
+    lat.close()
+
+
+def test_D_Ddag_DDdag_vs_reference(case):
+    lat, g = case
+    U, phi, m0 = g["U"], g["phi"], float(g["m0"])
+    assert relerr(lat.D_phi(U, phi, m0), g["D"]) <= TOL_D
+    assert relerr(lat.D_dagger_phi(U, phi, m0), g["Ddag"]) <= TOL_D
+    assert relerr(lat.D_D_dagger_phi(U, phi, m0), g["DDdag"]) <= TOL_D
+
+
+def test_dot_vs_reference(case):
+    lat, g = case
+    z = lat.dot(g["phi"], g["chi"])
+    want = complex(*g["dot"])
+    assert abs(z - want) <= 1e-13 * np.abs(g["phi"]).size
+
+
+def test_cg_vs_reference(case):
+    lat, g = case
+    x, ok, its = lat.conjugate_gradient(g["U"], g["phi"], float(g["m0"]))
+    assert ok == int(g["cg_ok"]) == 1
+    assert abs((its + 2) - int(g["cg_apps"])) <= 1       # DD^dagger applications = k + 2
+    assert relerr(x, g["cg_x"]) <= TOL_X
+    # true residual to the stated tolerance
+    r = g["phi"] - lat.D_D_dagger_phi(g["U"], x, float(g["m0"]))
+    assert np.linalg.norm(r) <= 2e-10 * np.linalg.norm(g["phi"])
+
+
+def test_forces_and_gauge_vs_reference(case):
+    lat, g = case
+    U, m0, beta = g["U"], float(g["m0"]), float(g["beta"])
+    x = g["cg_x"]
+    chi = lat.D_dagger_phi(U, x, m0)
+    assert relerr(lat.phi_dag_partialD_phi(U, x, chi), g["fforce"]) <= 1e-12
+    assert relerr(lat.Compute_Staple(U), g["staple"]) <= 1e-14
+    P, sp, sg = lat.Compute_Plaquette01(U, beta)
+    assert relerr(P, g["plaq"]) <= 1e-14
+    assert abs(sp - g["plaq_sums"][0]) <= 1e-12 * U.shape[1]
+    assert abs(sg - g["plaq_sums"][1]) <= 1e-12 * U.shape[1]
+    lat.hmc_configure(beta, m0, int(g["md"]), float(g["tau"]))
+    lat.hmc_set_gauge(U)
+    F, ok = lat.hmc_force(g["phi"])
+    assert ok == 1 and relerr(F, g["force"]) <= 1e-8
+
+
+def test_hamiltonian_leapfrog_trajectory_vs_reference(case):
+    lat, g = case
+    U, pi, phi, chi = g["U"], g["pi"], g["phi"], g["chi"]
+    m0, beta, md, tau = float(g["m0"]), float(g["beta"]), int(g["md"]), float(g["tau"])
+    lat.hmc_configure(beta, m0, md, tau)
+    lat.hmc_set_gauge(U)
+    H = lat.hmc_hamiltonian(pi, phi)
+    assert abs(H - float(g["hamiltonian"])) <= TOL_DH
+    Ul, pl, ok = lat.hmc_leapfrog(pi, phi)
+    assert ok == 1
+    assert np.abs(Ul - g["lf_U"]).max() <= 1e-9 and np.abs(pl - g["lf_pi"]).max() <= 1e-8
+    lat.hmc_inject(pi, chi)
+    r = lat.hmc_trajectory()
+    assert r.cg_all_converged == 1 and r.cg_solves == (md - 1) + 2
+    assert relerr(lat.hmc_get_phi(), g["tr_phi"]) <= TOL_D
+    assert np.abs(lat.hmc_get_gauge(True) - g["tr_U"]).max() <= 1e-9
+    assert np.abs(lat.hmc_get_momenta(True) - g["tr_pi"]).max() <= 1e-8
+    H_old, H_new = g["tr_H"]
+    assert abs(r.H_old - H_old) <= TOL_DH and abs(r.H_new - H_new) <= TOL_DH
+    assert abs(r.dH - (H_new - H_old)) <= TOL_DH
+    assert abs(r.sum_re_plaq_new - g["tr_aux"][0]) <= 1e-9 and abs(r.gauge_action_new - g["tr_aux"][1]) <= 1e-9
+    # accept swaps the proposal in; reject keeps U
+    lat.hmc_accept(False)
+    assert np.array_equal(lat.hmc_get_gauge(False), U)
+    lat.hmc_accept(True)
+    assert np.abs(lat.hmc_get_gauge(False) - g["tr_U"]).max() <= 1e-9
+
+
+def test_64x64_config1_vs_reference_fingerprints(sb):
+    """BASELINE config 1 size: CG on the hot start and one full trajectory (MD=10, tau=1, beta=2, m0=0)."""
+    from oracle.port import Port, gaussian_fields
+    s = np.load(os.path.join(GOLDEN, "ref_64x64_scalars.npz"))
+    lat = sb.Lattice(64, 64)
+    U = Port(64, 64).hot_start(12345)
+    chi, pi = gaussian_fields(64, 64, 777)
+    phi, _ = gaussian_fields(64, 64, 778)
+    x, ok, its = lat.conjugate_gradient(U, phi, 0.0)
+    assert ok == 1 and abs(its + 2 - int(s["cg_apps"])) <= 1
+    assert abs(np.linalg.norm(x) - float(s["cg_x_norm"])) <= 1e-9 * float(s["cg_x_norm"])
+    lat.hmc_configure(2.0, 0.0, 10, 1.0)
+    lat.hmc_set_gauge(U)
+    lat.hmc_inject(pi, chi)
+    r = lat.hmc_trajectory()
+    H_old, H_new = s["tr_H"]
+    assert abs(r.H_old - H_old) <= TOL_DH and abs(r.H_new - H_new) <= TOL_DH
+    assert abs(r.dH - (H_new - H_old)) <= TOL_DH
+    assert abs(r.sum_re_plaq_new - float(s["tr_sp"])) <= 1e-8
+    Un = lat.hmc_get_gauge(True)
+    assert abs(Un.sum() - complex(*s["tr_U_sum"])) <= 1e-8
+    lat.close()
+
+
+@pytest.mark.parametrize("nx,nt,m0", [(4, 4, 0.2), (2, 2, 0.5), (6, 40, 0.0), (40, 6, -0.1), (64, 256, 0.0), (130, 70, 0.1),
+                                      (256, 256, 0.0)])
+def test_shapes_vs_oracle(sb, nx, nt, m0):
+    """Tiny, ragged (partial tiles in both directions), non-square and config-2-sized lattices."""
+    from oracle.port import Port, gaussian_fields
+    P, lat = Port(nx, nt), sb.Lattice(nx, nt)
+    U = P.hot_start(4321)
+    phi, pi = gaussian_fields(nx, nt, 5)
+    assert relerr(lat.D_phi(U, phi, m0), P.D(U, phi, m0)) <= TOL_D
+    assert relerr(lat.D_dagger_phi(U, phi, m0), P.D(U, phi, m0, True)) <= TOL_D
+    assert relerr(lat.D_D_dagger_phi(U, phi, m0), P.DDdag(U, phi, m0)) <= TOL_D
+    z, w = lat.dot(phi, U), P.dot(phi, U)
+    assert abs(z - w) <= 1e-12 * nx * nt
+    x = P.cg(U, phi, m0)[0] if nx * nt <= 70000 else phi
+    chi = P.D(U, x, m0, True)
+    assert relerr(lat.phi_dag_partialD_phi(U, x, chi), P.fermion_force(U, x, chi)) <= 1e-12
+    assert relerr(lat.Compute_Staple(U), P.staple(U)) <= 1e-14
+    Pg, sp, sg = lat.Compute_Plaquette01(U, 2.0)
+    Po, spo, sgo = P.plaquette(U, 2.0)
+    assert relerr(Pg, Po) <= 1e-14 and abs(sp - spo) <= 1e-12 * nx * nt and abs(sg - sgo) <= 1e-12 * nx * nt
+    lat.close()
+
+
+def test_config2_cg_256_vs_oracle(sb):
+    """BASELINE config 2: one CG solve on the 256x256 hot start, m0 = 0."""
+    from oracle.port import Port, gaussian_fields
+    P, lat = Port(256, 256), sb.Lattice(256, 256)
+    U = P.hot_start(12345)
+    phi, _ = gaussian_fields(256, 256, 777)
+    xo, oko, apps, _ = P.cg(U, phi, 0.0)
+    x, ok, its = lat.conjugate_gradient(U, phi, 0.0)
+    assert ok == oko == 1 and abs(its + 2 - apps) <= 1
+    assert relerr(x, xo) <= TOL_X
+    lat.close()
+
+
+def test_cg_not_converged_returns_zero(sb):
+    from oracle.port import Port, gaussian_fields
+    P, lat = Port(16, 16), sb.Lattice(16, 16)
+    U = P.hot_start(1)
+    phi, _ = gaussian_fields(16, 16, 2)
+    for max_iter in (1, 5, 8, 9, 17):
+        lat.set_cg(1e-10, max_iter)
+        x, ok, its = lat.conjugate_gradient(U, phi, 0.0)
+        xo, oko, apps, _ = P.cg(U, phi, 0.0, 1e-10, max_iter)
+        assert ok == oko == 0 and its == max_iter and apps == max_iter + 1
+        assert relerr(x, xo) <= 1e-10
+    lat.set_cg(1e-3, 100)   # loose tolerance: stops early, same count as the oracle
+    x, ok, its = lat.conjugate_gradient(U, phi, 0.0)
+    xo, oko, apps, _ = P.cg(U, phi, 0.0, 1e-3, 100)
+    assert ok == oko == 1 and its + 2 == apps
+    lat.close()
+
+
+def test_device_resident_path_matches_host_path(sb):
+    from oracle.port import Port, gaussian_fields
+    nx, nt, m0 = 32, 48, -0.02
+    P, lat = Port(nx, nt), sb.Lattice(nx, nt)
+    U = P.hot_start(9)
+    phi, _ = gaussian_fields(nx, nt, 10)
+    dU, dphi, dout, dx = (lat.new_field(True, U), lat.new_field(True, phi), lat.new_field(), lat.new_field())
+    lat.dev_D(dU, dphi, dout, m0)
+    assert np.array_equal(dout.download(), lat.D_phi(U, phi, m0))
+    lat.dev_DDdag(dU, dphi, dout, m0)
+    assert np.array_equal(dout.download(), lat.D_D_dagger_phi(U, phi, m0))
+    ok, its = lat.dev_cg(dU, dphi, dx, m0)
+    x, ok2, its2 = lat.conjugate_gradient(U, phi, m0)
+    assert (ok, its) == (ok2, its2) and np.array_equal(dx.download(), x)
+    assert lat.dev_dot(dx, dphi) == lat.dot(x, phi)
+    ms = lat.dev_DDdag_loop(dU, dphi, dout, m0, 5)
+    assert ms > 0 and np.array_equal(dout.download(), lat.D_D_dagger_phi(U, phi, m0))
+    assert lat.launch_count() > 0
+    for f in (dU, dphi, dout, dx):
+        f.free()
+    lat.close()
+
+
+# ---- size-independent properties (also run at larger sizes) ------------------------------------
+
+@pytest.mark.parametrize("nx,nt", [(32, 32), (512, 512), (1024, 2048)])
+def test_adjointness_gamma5_linearity(sb, nx, nt):
+    from oracle.port import gaussian_fields
+    lat = sb.Lattice(nx, nt)
+    rng = np.random.default_rng(3)
+    U = np.exp(2j * np.pi * rng.random((2, nx * nt)))
+    a, _ = gaussian_fields(nx, nt, 11)
+    b, _ = gaussian_fields(nx, nt, 12)
+    m0 = -0.05
+    Da, Ddb = lat.D_phi(U, a, m0), lat.D_dagger_phi(U, b, m0)
+    lhs, rhs = lat.dot(Da, b), lat.dot(a, Ddb)
+    assert abs(lhs - rhs) <= 1e-12 * abs(lhs) + 1e-9
+    s3 = np.array([1.0, -1.0])[:, None]
+    assert relerr(s3 * lat.D_phi(U, s3 * a, m0), lat.D_dagger_phi(U, a, m0)) <= TOL_D
+    lin = lat.D_phi(U, 2.0 * a + (0.5 - 1j) * b, m0)
+    assert relerr(lin, 2.0 * Da + (0.5 - 1j) * lat.D_phi(U, b, m0)) <= 5e-13
+    # CG really inverts D D^dagger
+    lat.set_cg(1e-10, 10000)
+    x, ok, its = lat.conjugate_gradient(U, a, 0.1)
+    assert ok == 1
+    r = a - lat.D_D_dagger_phi(U, x, 0.1)
+    assert np.linalg.norm(r) <= 2e-10 * np.linalg.norm(a)
+    lat.close()
+
+
+def test_free_field_symbol(sb):
+    nx, nt, m0 = 8, 12, 0.3
+    lat = sb.Lattice(nx, nt)
+    U = np.ones((2, nx * nt), complex)
+    kx, kt = 3, 2
+    px, pt = 2 * np.pi * kx / nx, (2 * kt + 1) * np.pi / nt
+    x, t = np.divmod(np.arange(nx * nt), nt)
+    wave = np.exp(1j * (px * x + pt * t))
+    v = np.array([0.3 - 0.2j, 1.1 + 0.7j])
+    psi = v[:, None] * wave[None, :]
+    s0 = np.array([[0, 1], [1, 0]], complex)
+    s1 = np.array([[0, -1j], [1j, 0]], complex)
+    sym = (m0 + 2 - np.cos(pt) - np.cos(px)) * np.eye(2) + 1j * (s0 * np.sin(pt) + s1 * np.sin(px))
+    want = (sym @ v)[:, None] * wave[None, :]
+    assert np.abs(lat.D_phi(U, psi, m0) - want).max() < 1e-13
+    lat.close()
+
+
+def test_force_is_minus_dS_and_leapfrog_reversible(sb):
+    g = load_golden(8, 8)
+    lat = sb.Lattice(8, 8)
+    U, pi, phi = g["U"].copy(), g["pi"], g["phi"]
+    m0, beta = float(g["m0"]), float(g["beta"])
+    lat.set_cg(1e-13, 10000)
+    lat.hmc_configure(beta, m0, 6, 0.5)
+    lat.hmc_set_gauge(U)
+    F, _ = lat.hmc_force(phi)
+    zero = np.zeros_like(pi)
+    w = 1e-5
+    for mu, n in [(0, 3), (1, 5), (0, 63)]:
+        Up, Um = U.copy(), U.copy()
+        Up[mu, n] *= np.exp(1j * w)
+        Um[mu, n] *= np.exp(-1j * w)
+        lat.hmc_set_gauge(Up)
+        sp = lat.hmc_hamiltonian(zero, phi)
+        lat.hmc_set_gauge(Um)
+        sm = lat.hmc_hamiltonian(zero, phi)
+        dS = (sp - sm) / (2 * w)
+        assert abs(F[mu, n] + dS) < 2e-5 * max(1.0, abs(dS))
+    lat.hmc_set_gauge(U)
+    U1, p1, _ = lat.hmc_leapfrog(pi, phi)
+    lat.hmc_set_gauge(U1)
+    U2, p2, _ = lat.hmc_leapfrog(-p1, phi)
+    assert np.abs(U2 - U).max() < 1e-11 and np.abs(p2 + pi).max() < 1e-10
+    assert np.abs(np.abs(U1) - 1).max() < 1e-14
+    lat.close()
+
+
+def test_device_rng_moments_and_decomposition_independence(sb):
+    lat = sb.Lattice(256, 256)
+    lat.hmc_configure(2.0, 0.0, 4, 0.1)
+    lat.hmc_refresh(42, 0)
+    # fields are consumed by a trajectory; read them back through a trajectory-free path
+    pi = lat.hmc_get_momenta(False)
+    assert abs(pi.mean()) < 0.02 and abs(pi.std() - 1.0) < 0.02
+    lat.hmc_refresh(42, 1)
+    pi2 = lat.hmc_get_momenta(False)
+    assert not np.array_equal(pi, pi2)
+    lat.hmc_refresh(42, 0)
+    assert np.array_equal(pi, lat.hmc_get_momenta(False))
+    lat.close()
+
+
+def test_config_file_bytes_and_roundtrip(sb, tmp_path):
+    g = load_golden(8, 8)
+    f = tmp_path / "a.ctxt"
+    sb.SaveConf(g["U"], 8, 8, str(f))
+    want = open(os.path.join(GOLDEN, "ref_8x8.ctxt"), "rb").read()
+    assert f.read_bytes() == want
+    assert np.array_equal(sb.readBinary(8, 8, os.path.join(GOLDEN, "ref_8x8.ctxt")), g["U"])
+    with pytest.raises(sb.SchwingerError):
+        sb.readBinary(16, 16, str(f))      # short file
+
+
+def test_hmc_chain_statistics_64(sb):
+    """Physics smoke of SURVEY section 4: 64x64, beta=2, m0=0, MD=10, tau=1 -> <P> ~ 0.7187(11), acceptance ~0.65."""
+    from oracle.port import Port
+    lat = sb.Lattice(64, 64)
+    U = Port(64, 64).hot_start(12345)
+    h = sb.HMC(lat, U, 10, 1.0, 60, 20, 0, 2.0, 0.0, seed=7)
+    Ep, dEp = h.HMC_algorithm()
+    assert abs(Ep - 0.7187) < 0.02
+    assert 0.3 < h.getacceptance_rate() <= 1.0
+    assert all(ok for (_, _, _, ok, _) in h.history)
+    lat.close()
