@@ -1,0 +1,103 @@
+"""Split-lattice parity, one process per GPU:  torchrun --nproc-per-node N tests/dist/dist_check.py
+Every rank holds a tile; results are compared with the single-rank oracle on the global lattice
+(the reference's multi-rank code equals its single-rank code, tests/test_oracle_vs_reference.py)."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+import schwingermodel_b200 as sb  # noqa: E402
+from oracle.port import Port, gaussian_fields  # noqa: E402
+from schwingermodel_b200.tiles import tile_of  # noqa: E402
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    decomps = [(rx, world // rx) for rx in range(1, world + 1) if world % rx == 0]
+    nx, nt, m0, beta, md, tau = 32, 48, -0.05, 2.0, 5, 0.5
+    P = Port(nx, nt)
+    U = P.hot_start(12345)
+    chi, pi = gaussian_fields(nx, nt, 777)
+    phi, _ = gaussian_fields(nx, nt, 778)
+    want = dict(D=P.D(U, phi, m0), Ddag=P.D(U, phi, m0, True), DD=P.DDdag(U, phi, m0), dot=P.dot(phi, chi),
+                staple=P.staple(U))
+    xo, oko, apps, _ = P.cg(U, phi, m0)
+    want["ff"] = P.fermion_force(U, xo, P.D(U, xo, m0, True))
+    Pl, sp, sg = P.plaquette(U, beta)
+    F, _ = P.force(U, phi, beta, m0)
+    tr = P.trajectory(U, pi, chi, md, tau, beta, m0)
+    report = []
+    for rx, rt in decomps:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(sb.Lattice.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        lat = sb.Lattice(nx, nt, device=local, ranks_x=rx, ranks_t=rt, rank=rank, nccl_id=idt.cpu().numpy().tobytes())
+        T = lambda f: tile_of(f, nx, nt, rx, rt, rank)   # noqa: E731
+        tabs, otabs = lat.periodic_boundary(rx, rt, rank), P.tables(rx, rt, rank)
+        assert all(np.array_equal(tabs[k], otabs[k]) for k in tabs)
+        e = {}
+        e["D"] = rel(lat.D_phi(T(U), T(phi), m0), T(want["D"]))
+        e["Ddag"] = rel(lat.D_dagger_phi(T(U), T(phi), m0), T(want["Ddag"]))
+        e["DD"] = rel(lat.D_D_dagger_phi(T(U), T(phi), m0), T(want["DD"]))
+        z = lat.dot(T(phi), T(chi))
+        e["dot"] = abs(z - want["dot"]) / abs(want["dot"])
+        x, ok, its = lat.conjugate_gradient(T(U), T(phi), m0)
+        assert ok == 1 and abs(its + 2 - apps) <= 1, (ok, its, apps)
+        e["cg"] = rel(x, T(xo))
+        e["ff"] = rel(lat.phi_dag_partialD_phi(T(U), T(xo), T(P.D(U, xo, m0, True))), T(want["ff"]))
+        e["staple"] = rel(lat.Compute_Staple(T(U)), T(want["staple"]))
+        Pg, spg, sgg = lat.Compute_Plaquette01(T(U), beta)
+        e["plaq"] = rel(Pg[None, :], T(Pl[None, :]))
+        e["sp"] = abs(spg - sp) / abs(sp)
+        e["sg"] = abs(sgg - sg) / abs(sg)
+        lat.hmc_configure(beta, m0, md, tau)
+        lat.hmc_set_gauge(T(U))
+        Fg, fok = lat.hmc_force(T(phi))
+        e["force"] = rel(Fg, T(F))
+        lat.hmc_inject(T(pi), T(chi))
+        r = lat.hmc_trajectory()
+        e["dH"] = abs(r.dH - tr["dH"])
+        e["U'"] = float(np.abs(lat.hmc_get_gauge(True) - T(tr["U"])).max())
+        e["pi'"] = float(np.abs(lat.hmc_get_momenta(True) - T(tr["pi"])).max())
+        # device RNG is indexed by the global site: tiles of the same global field on every decomposition
+        lat.hmc_refresh(99, 3)
+        mine = lat.hmc_get_momenta(False)
+        ref = None
+        if rx * rt > 1:
+            one = sb.Lattice(nx, nt, device=local)
+            one.hmc_configure(beta, m0, md, tau)
+            one.hmc_refresh(99, 3)
+            ref = T(one.hmc_get_momenta(False))
+            one.close()
+            assert np.array_equal(mine, ref)
+        lat.close()
+        tol = dict(D=1e-13, Ddag=1e-13, DD=1e-13, dot=1e-12, cg=1e-9, ff=1e-12, staple=1e-14, plaq=1e-14, sp=1e-12,
+                   sg=1e-12, force=1e-8, dH=1e-8)
+        tol["U'"] = 1e-9
+        tol["pi'"] = 1e-8
+        bad = {k: v for k, v in e.items() if not v <= tol[k]}
+        report.append({"ranks_x": rx, "ranks_t": rt, "errors": e, "bad": bad})
+        assert not bad, (rx, rt, bad)
+        dist.barrier()
+    if rank == 0:
+        print(json.dumps({"world": world, "checked": report}))
+        print("DIST_CHECK_OK")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
