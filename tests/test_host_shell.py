@@ -88,7 +88,7 @@ def test_reference_cxx_interface_vs_oracle(tmp_path, nx, nt):
 def test_executable_protocol_and_outputs(tmp_path):
     """printf params | SM_16x24: prompts on stderr, banner/results on stdout, SimData + .ctxt files."""
     _build(16, 24)
-    params = "1\n1\n-0.05\n6\n0.6\n2\n5\n20\n0\n1\n"
+    params = "1\n1\n-0.05\n12\n0.6\n2\n40\n20\n0\n1\n"    # eps = 0.05: dH ~ 1 from the hot start
     env = dict(os.environ, SM_SEED="5", HOSTNAME="testhost")
     r = subprocess.run([os.path.join(BIN, "SM_16x24")], input=params, capture_output=True, text=True, cwd=tmp_path,
                        env=env, timeout=600)
@@ -103,9 +103,9 @@ def test_executable_protocol_and_outputs(tmp_path):
     assert sim[4] == "#Nx      #Nt" and sim[5] == f"{16:>10}{24:>10}"
     assert sim[-8] == "#Ep                           #dEp" and sim[-2] == "#Execution time"
     ep = float(sim[-7].split()[0])
-    assert 0.3 < ep < 0.95
     acc = float(sim[-3])
-    assert 0.0 <= acc <= 1.0
+    assert 0.0 < acc <= 1.0
+    assert 0.3 < ep < 0.95
     confs = sorted(p.name for p in tmp_path.glob("2D_U1_Ns16_Nt24_b20000_m-00500_*.ctxt"))
     assert len(confs) == 20
     raw = (tmp_path / confs[-1]).read_bytes()
