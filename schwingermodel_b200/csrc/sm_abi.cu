@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "sm_kernels.cuh"
+#include "sm_fused.cuh"
 
 using namespace sm;
 
@@ -105,6 +106,10 @@ struct sm_ctx {
     // launch geometry
     dim3 wil_block, wil_grid;
     int rows_per_block = 0;
+    dim3 fus_block, fus_grid;   // one-pass D D^dagger (sm_fused.cuh)
+    int fus_rows = 0, fus_cols = 0;
+    size_t fus_smem = 0;
+    bool use_fused = true;      // SM_DD_PATH=twopass selects the two-pass form
     int flat_blocks_c = 0;   // grid for flat passes over 2V elements
     int flat_blocks_s = 0;   // grid for passes over V sites
 
@@ -120,7 +125,7 @@ struct sm_ctx {
     int max_iter = 10000;
 
     // work fields (2V complex each)
-    cplx *tmp = nullptr, *cg_r = nullptr, *cg_d = nullptr, *cg_Ad = nullptr;
+    cplx *tmp = nullptr, *cg_r = nullptr, *cg_d = nullptr, *cg_Ad = nullptr, *cg_d2 = nullptr;
     // staging for the host-buffer API
     cplx *sU = nullptr, *sA = nullptr, *sB = nullptr, *sC = nullptr;
     double* sF = nullptr;
@@ -198,11 +203,34 @@ static int ctx_common_init(sm_ctx* c) {
     c->rows_per_block = rows;
     c->wil_grid = dim3(nT, GY, 1);
 
+    // one-pass D D^dagger: strips of BT-4 columns, chunks of rows; ~8 waves of 2 blocks per SM
+    {
+        const int BT = c->wt + 4 <= 128 ? 128 : 256;
+        const int strips = (c->wt + (BT - 4) - 1) / (BT - 4);
+        c->fus_cols = (c->wt + strips - 1) / strips;     // equal strips
+        const int want_blocks = c->sm_count * 2 * 8;
+        int chunks = std::max(1, std::min(c->wx, want_blocks / strips));
+        int rows = (c->wx + chunks - 1) / chunks;
+        rows = std::max(rows, std::min(c->wx, 32));      // keep the 4-row warm-up overhead <= 12 %
+        chunks = (c->wx + rows - 1) / rows;
+        c->fus_block = dim3(BT, 1, 1);
+        c->fus_grid = dim3(strips, chunks, 1);
+        c->fus_rows = rows;
+        c->fus_smem = sizeof(cplx) * 2 * 4 * BT;
+        const char* e = getenv("SM_DD_PATH");
+        c->use_fused = !(e && std::string(e) == "twopass");
+        if (const char* r = getenv("SM_FUSED_ROWS")) {
+            c->fus_rows = std::max(1, std::min(c->wx, atoi(r)));
+            c->fus_grid.y = (c->wx + c->fus_rows - 1) / c->fus_rows;
+        }
+    }
+
     const int cap = c->sm_count * 8;
     c->flat_blocks_c = std::max(1, std::min(cap, (2 * c->V + kBlock - 1) / kBlock));
     c->flat_blocks_s = std::max(1, std::min(cap, (c->V + kBlock - 1) / kBlock));
 
-    const size_t max_blocks = std::max<size_t>((size_t)nT * GY, (size_t)cap);
+    const size_t max_blocks = std::max<size_t>(std::max<size_t>((size_t)nT * GY, (size_t)cap),
+                                               (size_t)c->fus_grid.x * c->fus_grid.y);
     TRY(dev_alloc(&c->partials, max_blocks * kMaxSums));
     TRY(dev_alloc(&c->tickets, (size_t)TK_COUNT));
     CU(cudaMemsetAsync(c->tickets, 0, sizeof(unsigned int) * TK_COUNT, c->stream));
@@ -326,7 +354,44 @@ static int dev_D(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, double m0,
 }
 
 // D D^dagger via the context's scratch field (the reference's global DTEMP, dirac_operator.cpp:477-480)
+// one-pass D D^dagger (sm_fused.cuh); single-tile lattices only (a split lattice would need 2-deep ghosts)
+template <int MODE>
+static int launch_fused(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, double m0, double* sums_out = nullptr,
+                        const cplx* r = nullptr, cplx* x = nullptr, cplx* d_new = nullptr, int k = 0) {
+    FusedArgs a{};
+    a.U = U;
+    a.in = in;
+    a.out = out;
+    a.wx = c->wx;
+    a.wt = c->wt;
+    a.V = c->V;
+    a.rows_per_block = c->fus_rows;
+    a.cols_per_strip = c->fus_cols;
+    a.mass = m0 + 2;
+    a.sR_edge = c->sR_edge();
+    a.sL_edge = c->sL_edge();
+    a.partials = c->partials;
+    a.ticket = c->tickets + TK_WILSON;
+    a.sums_out = sums_out;
+    a.st = c->cg;
+    a.r = r;
+    a.x = x;
+    a.d_new = d_new;
+    a.k = k;
+    a.tol = c->tol;
+    k_dd_fused<MODE><<<c->fus_grid, c->fus_block, c->fus_smem, c->stream>>>(a);
+    KCHECK();
+    c->launches++;
+    return SM_OK;
+}
+
+static bool fused_ok(const sm_ctx* c) { return c->use_fused && !c->dist(); }
+
+// D D^dagger: one pass over HBM on a single tile, else D^dagger then D through the context's
+// scratch field (the reference's global DTEMP, dirac_operator.cpp:477-480)
 static int dev_DDdag(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, double m0) {
+    if (in == out) return fail(SM_ERR_ARG, "D D^dagger: in and out must not alias");
+    if (fused_ok(c)) return launch_fused<FUSED_PLAIN>(c, U, in, out, m0);
     TRY(ensure_complex(c, &c->tmp));
     TRY(dev_D(c, U, in, c->tmp, m0, true));
     return dev_D(c, U, c->tmp, out, m0, false);
@@ -344,7 +409,7 @@ static int dev_dot_async(sm_ctx* c, const cplx* x, const cplx* y, double* d_out2
 // enqueues batches of iterations and polls a pinned copy of the CG scalars one batch behind, so
 // the GPU never waits for it; once the stopping rule has fired every later kernel of the queue
 // returns at its first instruction.
-static int dev_cg(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, int* converged, int* iterations) {
+static int dev_cg_twopass(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, int* converged, int* iterations) {
     TRY(ensure_complex(c, &c->tmp));
     TRY(ensure_complex(c, &c->cg_r));
     TRY(ensure_complex(c, &c->cg_d));
@@ -407,6 +472,68 @@ static int dev_cg(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0,
     if (converged) *converged = c->h->cg[0].converged;
     if (iterations) *iterations = c->h->cg[0].iters;
     return SM_OK;
+}
+
+// The same algorithm on the one-pass D D^dagger: per iteration k
+//   A(k): stopping rule of k-1 ; d_k = r_k + beta d_{k-1} ; x += alpha_{k-1} d_{k-1} ; Ad = D D^dagger d_k ; dot(d_k, Ad)
+//   B(k): alpha_k = r_norm2 / dot ; r -= alpha_k Ad ; |r|^2
+// and one k_cg_flush_x at the end for the x update the loop still owes.  320 B per site and iteration.
+static int dev_cg_fused(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, int* converged, int* iterations) {
+    TRY(ensure_complex(c, &c->tmp));
+    TRY(ensure_complex(c, &c->cg_r));
+    TRY(ensure_complex(c, &c->cg_d));
+    TRY(ensure_complex(c, &c->cg_d2));
+    TRY(ensure_complex(c, &c->cg_Ad));
+    const int n_elems = 2 * c->V;
+    const double tol = c->tol;
+    const int max_iter = c->max_iter;
+    CgState* st = c->cg;
+    cplx* dbuf[2] = {c->cg_d, c->cg_d2};
+
+    k_cg_reset<<<1, 1, 0, c->stream>>>(st);
+    c->launches++;
+    // x = phi ; r = phi - D D^dagger phi ; |phi|^2, |r|^2   (d_0 = r_0 is formed by A(0))
+    TRY((launch_wilson<true, WILSON_PLAIN>(c, U, phi, c->tmp, m0)));
+    TRY((launch_wilson<false, WILSON_CGINIT>(c, U, c->tmp, nullptr, m0, phi, c->cg_r, c->cg_d2, x, &st->phi_norm2)));
+
+    const int batch = 8;
+    int k = 0, slot = 0, prev = -1;
+    for (;;) {
+        const int k_end = std::min(max_iter, k + batch);
+        for (; k < k_end; k++) {
+            const int cur = k & 1;
+            TRY((launch_fused<FUSED_CG>(c, U, dbuf[cur ^ 1], c->cg_Ad, m0, st->dAd, c->cg_r, x, dbuf[cur], k)));
+            k_cg_resid<<<c->flat_blocks_c, kBlock, 0, c->stream>>>(st, cur, c->cg_r, c->cg_Ad, n_elems, c->partials,
+                                                                   c->tickets + TK_UPDATE, &st->rr[cur ^ 1]);
+            KCHECK();
+            c->launches++;
+        }
+        k_cg_check<<<1, 1, 0, c->stream>>>(st, k, tol, max_iter);
+        KCHECK();
+        c->launches++;
+        CU(cudaMemcpyAsync(&c->h->cg[slot], st, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaEventRecord(c->ev_poll[slot], c->stream));
+        if (prev >= 0) {
+            CU(cudaEventSynchronize(c->ev_poll[prev]));
+            if (c->h->cg[prev].done) break;
+        }
+        if (k >= max_iter) break;
+        prev = slot;
+        slot ^= 1;
+    }
+    k_cg_flush_x<<<c->flat_blocks_c, kBlock, 0, c->stream>>>(st, x, dbuf[0], dbuf[1], n_elems);
+    KCHECK();
+    c->launches++;
+    CU(cudaMemcpyAsync(&c->h->cg[0], st, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (converged) *converged = c->h->cg[0].converged;
+    if (iterations) *iterations = c->h->cg[0].iters;
+    return SM_OK;
+}
+
+static int dev_cg(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, int* converged, int* iterations) {
+    if (fused_ok(c)) return dev_cg_fused(c, U, phi, x, m0, converged, iterations);
+    return dev_cg_twopass(c, U, phi, x, m0, converged, iterations);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -819,7 +946,7 @@ int sm_destroy(sm_ctx* c) {
     cudaStreamSynchronize(c->stream);
     if (c->comm) g_nccl.CommDestroy(c->comm);
     void* ptrs[] = {c->partials, c->tickets, c->cg,      c->sums,    c->sums_loc, c->tmp,     c->cg_r,   c->cg_d,
-                    c->cg_Ad,    c->sU,      c->sA,      c->sB,      c->sC,       c->sF,      c->U,      c->Up,
+                    c->cg_Ad,    c->cg_d2, c->sU,      c->sA,      c->sB,      c->sC,       c->sF,      c->U,      c->Up,
                     c->chi,      c->phi,     c->psi,     c->xi,      c->pi,       c->pip,     c->F,      c->send_tm,
                     c->send_tp,  c->send_xm, c->send_xp, c->g_tp,    c->g_tm,     c->g_xp,    c->g_xm,   c->gg_xm,
                     c->gg_xp,    c->gg_tm,   c->gg_tp,   c->gg_send, c->fg_t,     c->fg_x,    c->fg_send};

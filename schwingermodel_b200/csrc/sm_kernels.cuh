@@ -53,10 +53,12 @@ struct CgState {
     double phi_norm2;   // Re dot(phi,phi)
     double rr[2];       // r_norm2, ping-pong on the iteration parity
     double dAd[2];      // dot(d, Ad), complex
-    double spare;
+    double alpha[2];    // alpha of the last residual update (fused path: x still lacks alpha d)
     int done;           // sticky: set once the stopping rule fired
     int iters;          // the reference's k when it returned
     int converged;      // the reference's return value
+    int pending;        // fused path: an x update is owed
+    int pending_buf;    // ... with d in ping-pong buffer 0/1
     int pad;
 };
 
@@ -358,6 +360,8 @@ __global__ void k_cg_reset(CgState* st) {
     st->done = 0;
     st->iters = 0;
     st->converged = 0;
+    st->pending = 0;
+    st->pending_buf = 0;
 }
 
 // dot(x,y) = sum x conj(y) over both components (include/variables.h:181-192)

@@ -340,3 +340,32 @@ def test_hmc_chain_statistics_64(sb):
     assert 0.3 < h.getacceptance_rate() <= 1.0
     assert all(ok for (_, _, _, ok, _) in h.history)
     lat.close()
+
+
+def test_one_pass_and_two_pass_DDdag_agree(sb):
+    """The temporally blocked D D^dagger (sm_fused.cuh) against D^dagger-then-D (k_wilson twice), and the
+    CG built on each, on ragged strips/chunks."""
+    from oracle.port import Port, gaussian_fields
+    for nx, nt, m0 in [(8, 8, 0.1), (37, 300, -0.02), (300, 37, 0.0), (64, 64, 0.0), (257, 509, 0.05)]:
+        P = Port(nx, nt)
+        U = P.hot_start(77)
+        phi, _ = gaussian_fields(nx, nt, 78)
+        os.environ["SM_DD_PATH"] = "twopass"
+        two = sb.Lattice(nx, nt)
+        os.environ.pop("SM_DD_PATH")
+        one = sb.Lattice(nx, nt)
+        a, b = one.D_D_dagger_phi(U, phi, m0), two.D_D_dagger_phi(U, phi, m0)
+        assert relerr(a, b) <= 1e-14, (nx, nt)
+        assert relerr(a, P.DDdag(U, phi, m0)) <= TOL_D
+        xa, oka, ia = one.conjugate_gradient(U, phi, m0)
+        xb, okb, ib = two.conjugate_gradient(U, phi, m0)
+        assert oka == okb == 1 and abs(ia - ib) <= 1
+        assert relerr(xa, xb) <= TOL_X
+        for rows in (1, 3):      # extreme chunking: every row is a warm-up row of some block
+            os.environ["SM_FUSED_ROWS"] = str(rows)
+            tiny = sb.Lattice(nx, nt)
+            os.environ.pop("SM_FUSED_ROWS")
+            assert relerr(tiny.D_D_dagger_phi(U, phi, m0), b) <= 1e-14
+            tiny.close()
+        one.close()
+        two.close()
