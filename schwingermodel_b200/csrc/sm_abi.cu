@@ -108,7 +108,6 @@ struct sm_ctx {
     int rows_per_block = 0;
     dim3 fus_block, fus_grid;   // one-pass D D^dagger (sm_fused.cuh)
     int fus_rows = 0, fus_cols = 0;
-    size_t fus_smem = 0;
     bool use_fused = true;      // SM_DD_PATH=twopass selects the two-pass form
     int flat_blocks_c = 0;   // grid for flat passes over 2V elements
     int flat_blocks_s = 0;   // grid for passes over V sites
@@ -203,26 +202,29 @@ static int ctx_common_init(sm_ctx* c) {
     c->rows_per_block = rows;
     c->wil_grid = dim3(nT, GY, 1);
 
-    // one-pass D D^dagger: strips of BT-4 columns, chunks of rows; ~8 waves of 2 blocks per SM
+    // one-pass D D^dagger: strips of <= BT-4 columns, chunks of rows.  Large lattices: ~8 waves of
+    // blocks with >= 64 rows each (4 warm-up rows per chunk); mid-size: one resident wave.
     {
-        const int BT = c->wt + 4 <= 128 ? 128 : 256;
+        const long long V = (long long)c->wx * c->wt;
+        int BT = (c->wt + 4 <= 128 || V <= (1LL << 22)) ? 128 : 256;
+        if (const char* e = getenv("SM_FUSED_BT")) BT = atoi(e) == 128 ? 128 : 256;
         const int strips = (c->wt + (BT - 4) - 1) / (BT - 4);
         c->fus_cols = (c->wt + strips - 1) / strips;     // equal strips
-        const int want_blocks = c->sm_count * 2 * 8;
-        int chunks = std::max(1, std::min(c->wx, want_blocks / strips));
-        int rows = (c->wx + chunks - 1) / chunks;
-        rows = std::max(rows, std::min(c->wx, 32));      // keep the 4-row warm-up overhead <= 12 %
-        chunks = (c->wx + rows - 1) / rows;
-        c->fus_block = dim3(BT, 1, 1);
-        c->fus_grid = dim3(strips, chunks, 1);
-        c->fus_rows = rows;
-        c->fus_smem = sizeof(cplx) * 2 * 4 * BT;
-        const char* e = getenv("SM_DD_PATH");
-        c->use_fused = !(e && std::string(e) == "twopass");
-        if (const char* r = getenv("SM_FUSED_ROWS")) {
-            c->fus_rows = std::max(1, std::min(c->wx, atoi(r)));
-            c->fus_grid.y = (c->wx + c->fus_rows - 1) / c->fus_rows;
+        const int capacity = c->sm_count * (BT == 128 ? 4 : 2);
+        int rows = (c->wx + std::max(1, 8 * capacity / strips) - 1) / std::max(1, 8 * capacity / strips);
+        if (rows < 64) {
+            const int chunks1 = std::max(1, capacity / strips);
+            rows = std::max(std::min(c->wx, 8), (c->wx + chunks1 - 1) / chunks1);
         }
+        if (const char* r = getenv("SM_FUSED_ROWS")) rows = std::max(1, std::min(c->wx, atoi(r)));
+        c->fus_block = dim3(BT, 1, 1);
+        c->fus_grid = dim3(strips, (c->wx + rows - 1) / rows, 1);
+        c->fus_rows = rows;
+        long long min_sites = 1LL << 18;                 // below this the two-pass kernels win (one site per thread)
+        if (const char* m = getenv("SM_FUSED_MIN_SITES")) min_sites = atoll(m);
+        const char* e = getenv("SM_DD_PATH");
+        c->use_fused = !(e && std::string(e) == "twopass") && V >= min_sites;
+        if (e && std::string(e) == "onepass") c->use_fused = true;
     }
 
     const int cap = c->sm_count * 8;
@@ -379,7 +381,14 @@ static int launch_fused(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, dou
     a.d_new = d_new;
     a.k = k;
     a.tol = c->tol;
-    k_dd_fused<MODE><<<c->fus_grid, c->fus_block, c->fus_smem, c->stream>>>(a);
+    constexpr int STAGES = (MODE == FUSED_CG) ? 2 : 3;
+    const size_t smem = fused_smem_bytes(MODE, STAGES, c->fus_block.x);
+    static bool attr_set = false;   // per instantiation
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(k_dd_fused<MODE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    k_dd_fused<MODE, STAGES><<<c->fus_grid, c->fus_block, smem, c->stream>>>(a);
     KCHECK();
     c->launches++;
     return SM_OK;

@@ -55,6 +55,8 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NS], double* __restrict_
     __shared__ double s_part[kWarps][NS];
     __shared__ bool s_last;
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int nthreads = blockDim.x * blockDim.y;      // a multiple of 32, at most kBlock
+    const int nwarps = nthreads >> 5;
     const int lane = tid & 31, warp = tid >> 5;
     const int nblocks = gridDim.x * gridDim.y;
     const int bid = blockIdx.y * gridDim.x + blockIdx.x;
@@ -68,7 +70,7 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NS], double* __restrict_
     if (warp == 0) {
 #pragma unroll
         for (int j = 0; j < NS; j++) {
-            double x = (lane < kWarps) ? s_part[lane][j] : 0.0;
+            double x = (lane < nwarps) ? s_part[lane][j] : 0.0;
             x = warp_sum(x);
             if (lane == 0) partials[NS * bid + j] = x;
         }
@@ -84,7 +86,7 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NS], double* __restrict_
 #pragma unroll
     for (int j = 0; j < NS; j++) {
         double x = 0.0;
-        for (int b = tid; b < nblocks; b += kBlock) x += __ldcg(&partials[NS * b + j]);
+        for (int b = tid; b < nblocks; b += nthreads) x += __ldcg(&partials[NS * b + j]);
         v[j] = warp_sum(x);
     }
     __syncthreads();   // s_part reuse
@@ -96,7 +98,7 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NS], double* __restrict_
     if (warp == 0) {
 #pragma unroll
         for (int j = 0; j < NS; j++) {
-            double x = (lane < kWarps) ? s_part[lane][j] : 0.0;
+            double x = (lane < nwarps) ? s_part[lane][j] : 0.0;
             v[j] = warp_sum(x);
         }
         if (lane == 0) *ticket = 0u;   // ready for the next launch

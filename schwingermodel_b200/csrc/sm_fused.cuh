@@ -6,7 +6,9 @@
 //     psi rows j-2, j-1, j      t rows j-3, j-2, j-1      and the links of those rows
 // in REGISTERS; the t-direction neighbours travel through a small double-buffered shared-memory
 // line of pre-projected half-spinors (the same rank-1 trick the halo exchange uses), one
-// __syncthreads per row.  Each step loads row j, forms t(j-1) = D^dagger psi and
+// __syncthreads per row.  Rows are staged from HBM into a shared-memory ring with cp.async
+// (16 B per thread and array, L1 bypassed, STAGES-1 rows in flight per block) so the loads never
+// occupy registers or stall the step.  Each step takes row j, forms t(j-1) = D^dagger psi and
 // out(j-2) = D t, so psi and U are read once and out is written once: ~96 B per site-update
 // plus the halo overhead (2 columns each side of a (BT-4)-wide strip, 4 rows per chunk).
 //
@@ -64,13 +66,34 @@ __device__ __forceinline__ int wrap_idx(int a, int n) {
     return a < 0 ? a + n : a;
 }
 
-// shared line: 4 complex per column and parity (fwd/bwd half-spinors of psi row and of t row)
-template <int MODE>
+// cp.async (LDGSTS): 16 bytes global -> shared without passing through registers, L1 bypassed
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__host__ __device__ constexpr int fused_arrays(int mode) { return mode == FUSED_CG ? 8 : 4; }
+constexpr size_t fused_smem_bytes(int mode, int stages, int BT) {
+    return sizeof(cplx) * (size_t)BT * (2 * 4 + (size_t)stages * fused_arrays(mode));
+}
+
+// Shared memory:  line  [2 parities][4][BT]   t-direction half-spinors of the psi row and the t row
+//                 stage [STAGES][NARR][BT]    rows in flight (each thread stages its own column:
+//                                             cp.async, no block barrier needed for it)
+template <int MODE, int STAGES>
 __global__ void __launch_bounds__(kBlock, 2) k_dd_fused(const FusedArgs a) {
-    extern __shared__ double2 s_line[];   // [2 parities][4][BT]
+    extern __shared__ double2 s_mem[];
+    constexpr int NARR = fused_arrays(MODE);
     const int BT = blockDim.x;
     const int tid = threadIdx.x;
     const int wt = a.wt, wx = a.wx, V = a.V;
+    double2* const s_line = s_mem;
+    double2* const s_stage = s_mem + 2 * 4 * BT;
 
     double beta = 0.0;
     cplx alpha = make_double2(0.0, 0.0);
@@ -102,63 +125,70 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_fused(const FusedArgs a) {
     const int xa = blockIdx.y * a.rows_per_block;
     const int xb = min(wx, xa + a.rows_per_block);
     const int tl = (tid == 0) ? 0 : tid - 1, tr = (tid == BT - 1) ? tid : tid + 1;
-
-    const cplx* __restrict__ in0 = a.in;
-    const cplx* __restrict__ in1 = a.in + V;
-    const cplx* __restrict__ U0 = a.U;
-    const cplx* __restrict__ U1 = a.U + V;
+    const int j_first = xa - 2, j_last = xb + 1;
 
     const cplx zero = make_double2(0.0, 0.0);
+    if (!col_active) {
+        for (int q = 0; q < STAGES * NARR; q++) s_stage[q * BT + tid] = zero;   // read back as zeros
+    }
+
+    // stage row j: psi (or r, d_{k-1}, x) and the links of this thread's column
+    auto issue_row = [&](int j) {
+        if (col_active && j <= j_last) {
+            double2* st = s_stage + ((j - j_first) % STAGES) * NARR * BT + tid;
+            const int n = wrap_idx(j, wx) * wt + t;
+            cp_async16(st + 0 * BT, a.U + n);
+            cp_async16(st + 1 * BT, a.U + V + n);
+            if (MODE != FUSED_CG) {
+                cp_async16(st + 2 * BT, a.in + n);
+                cp_async16(st + 3 * BT, a.in + V + n);
+            } else {
+                cp_async16(st + 2 * BT, a.r + n);
+                cp_async16(st + 3 * BT, a.r + V + n);
+                if (!first) {
+                    cp_async16(st + 4 * BT, a.in + n);
+                    cp_async16(st + 5 * BT, a.in + V + n);
+                    if (col_owner && j >= xa && j < xb) {
+                        cp_async16(st + 6 * BT, a.x + n);
+                        cp_async16(st + 7 * BT, a.x + V + n);
+                    }
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
     // psi rows (m2 = j-2, m1 = j-1), t rows (t3 = j-3, t2 = j-2), links
     cplx pm2_0 = zero, pm2_1 = zero, pm1_0 = zero, pm1_1 = zero;
     cplx t3_0 = zero, t3_1 = zero, t2_0 = zero, t2_1 = zero;
     cplx u0m2 = zero, u0m1 = zero, u1m3 = zero, u1m2 = zero, u1m1 = zero;
     double acc[2] = {0.0, 0.0};
 
-    // row loader: psi (or d_k formed from r and d_{k-1}) and links of row j
-    auto load_row = [&](int j, cplx& p0, cplx& p1, cplx& v0, cplx& v1) {
-        if (!col_active) {
-            p0 = p1 = v0 = v1 = zero;
-            return;
-        }
-        const int x = wrap_idx(j, wx);
-        const int n = x * wt + t;
-        v0 = ldg(U0 + n);
-        v1 = ldg(U1 + n);
-        if (MODE != FUSED_CG) {
-            p0 = ldg(in0 + n);
-            p1 = ldg(in1 + n);
-        } else {
-            const cplx r0 = ldg(a.r + n), r1 = ldg(a.r + V + n);
-            if (first) {
-                p0 = r0;
-                p1 = r1;
-            } else {
-                const cplx d0 = ldg(in0 + n), d1 = ldg(in1 + n);
-                p0 = make_double2(d0.x * beta + r0.x, d0.y * beta + r0.y);
-                p1 = make_double2(d1.x * beta + r1.x, d1.y * beta + r1.y);
-                if (col_owner && j >= xa && j < xb) {       // x += alpha_{k-1} d_{k-1}
-                    cplx x0 = a.x[n], x1 = a.x[V + n];
-                    x0 = cadd(x0, cmul(alpha, d0));
-                    x1 = cadd(x1, cmul(alpha, d1));
-                    a.x[n] = x0;
-                    a.x[V + n] = x1;
-                }
-            }
-            if (col_owner && j >= xa && j < xb) {
-                a.d_new[n] = p0;
-                a.d_new[V + n] = p1;
+#pragma unroll
+    for (int q = 0; q < STAGES - 1; q++) issue_row(j_first + q);
+
+    for (int j = j_first; j <= j_last; j++) {
+        issue_row(j + STAGES - 1);        // into the stage consumed at step j-1 (by this same thread)
+        cp_async_wait<STAGES - 1>();      // row j has landed; rows j+1 .. j+STAGES-1 may still fly
+        const double2* st = s_stage + ((j - j_first) % STAGES) * NARR * BT + tid;
+        const cplx v0 = st[0 * BT], v1 = st[1 * BT];
+        cplx p0 = st[2 * BT], p1 = st[3 * BT];
+        if (MODE == FUSED_CG && !first) {
+            // d_k = r_k + beta d_{k-1}  (conjugate_gradient.cpp:54-59), also at the halo sites
+            const cplx d0 = st[4 * BT], d1 = st[5 * BT];
+            p0 = make_double2(d0.x * beta + p0.x, d0.y * beta + p0.y);
+            p1 = make_double2(d1.x * beta + p1.x, d1.y * beta + p1.y);
+            if (col_owner && j >= xa && j < xb) {            // x += alpha_{k-1} d_{k-1}  (:34-36)
+                const int n = j * wt + t;
+                a.x[n] = cadd(st[6 * BT], cmul(alpha, d0));
+                a.x[V + n] = cadd(st[7 * BT], cmul(alpha, d1));
             }
         }
-    };
-
-    cplx p0, p1, v0, v1;           // row j
-    cplx np0, np1, nv0, nv1;       // row j+1 (prefetch)
-    load_row(xa - 2, np0, np1, nv0, nv1);
-
-    for (int j = xa - 2; j <= xb + 1; j++) {
-        p0 = np0; p1 = np1; v0 = nv0; v1 = nv1;
-        if (j < xb + 1) load_row(j + 1, np0, np1, nv0, nv1);
+        if (MODE == FUSED_CG && col_owner && j >= xa && j < xb) {
+            const int n = j * wt + t;
+            a.d_new[n] = p0;
+            a.d_new[V + n] = p1;
+        }
 
         // publish the t-direction half-spinors of psi row j-1 (for D^dagger) and t row j-2 (for D)
         double2* line = s_line + (j & 1) * 4 * BT;
@@ -189,8 +219,8 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_fused(const FusedArgs a) {
             const cplx o0 = make_double2(a.mass * t2_0.x - 0.5 * a0.x, a.mass * t2_0.y - 0.5 * a0.y);
             const cplx o1 = make_double2(a.mass * t2_1.x - 0.5 * a1.x, a.mass * t2_1.y - 0.5 * a1.y);
             const int n = (j - 2) * wt + t;      // xa <= j-2 < xb: no wrap
-            a.out[n] = o0;
-            a.out[V + n] = o1;
+            st_stream(a.out + n, o0);
+            st_stream(a.out + V + n, o1);
             if (MODE != FUSED_PLAIN) {           // dot(psi, out) = sum psi conj(out)
                 const cplx q0 = cmul_conj(pm2_0, o0), q1 = cmul_conj(pm2_1, o1);
                 acc[0] += q0.x + q1.x;

@@ -352,8 +352,9 @@ def test_one_pass_and_two_pass_DDdag_agree(sb):
         phi, _ = gaussian_fields(nx, nt, 78)
         os.environ["SM_DD_PATH"] = "twopass"
         two = sb.Lattice(nx, nt)
-        os.environ.pop("SM_DD_PATH")
+        os.environ["SM_DD_PATH"] = "onepass"
         one = sb.Lattice(nx, nt)
+        os.environ.pop("SM_DD_PATH")
         a, b = one.D_D_dagger_phi(U, phi, m0), two.D_D_dagger_phi(U, phi, m0)
         assert relerr(a, b) <= 1e-14, (nx, nt)
         assert relerr(a, P.DDdag(U, phi, m0)) <= TOL_D
@@ -362,9 +363,10 @@ def test_one_pass_and_two_pass_DDdag_agree(sb):
         assert oka == okb == 1 and abs(ia - ib) <= 1
         assert relerr(xa, xb) <= TOL_X
         for rows in (1, 3):      # extreme chunking: every row is a warm-up row of some block
-            os.environ["SM_FUSED_ROWS"] = str(rows)
+            os.environ.update(SM_FUSED_ROWS=str(rows), SM_DD_PATH="onepass", SM_FUSED_BT="256" if rows == 3 else "128")
             tiny = sb.Lattice(nx, nt)
-            os.environ.pop("SM_FUSED_ROWS")
+            for k in ("SM_FUSED_ROWS", "SM_DD_PATH", "SM_FUSED_BT"):
+                os.environ.pop(k)
             assert relerr(tiny.D_D_dagger_phi(U, phi, m0), b) <= 1e-14
             tiny.close()
         one.close()
