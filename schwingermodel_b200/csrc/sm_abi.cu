@@ -143,6 +143,10 @@ struct sm_ctx {
     cplx *gg_xm = nullptr, *gg_xp = nullptr, *gg_tm = nullptr, *gg_tp = nullptr, *gg_send = nullptr;
     cplx *fg_t = nullptr, *fg_x = nullptr, *fg_send = nullptr;
     const cplx* ghost_valid_for = nullptr;   // gauge field whose ghost ring is current
+    // 2-row ghosts for the one-pass D D^dagger on a lattice split along x ([comp][2 rows][wt] each)
+    cplx *f2_U[2] = {nullptr, nullptr}, *f2_in[2] = {nullptr, nullptr}, *f2_r[2] = {nullptr, nullptr};
+    cplx *f2_d[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [ping-pong][lo/hi]
+    const cplx* f2_U_valid_for = nullptr;
 
     std::vector<void*> user_fields;
 
@@ -266,6 +270,12 @@ static int tock(sm_ctx* c) {
 // ------------------------------------------------------------------------------------------------
 // split lattice: halo exchange of projected half-spinors, all-reduce of sums
 // ------------------------------------------------------------------------------------------------
+// ghost copies of a gauge field go stale whenever the field is written
+static void invalidate_gauge_ghosts(sm_ctx* c, const cplx* U) {
+    if (c->ghost_valid_for == U) c->ghost_valid_for = nullptr;
+    if (c->f2_U_valid_for == U) c->f2_U_valid_for = nullptr;
+}
+
 static int allreduce_sums(sm_ctx* c, const double* loc, double* glob, int n) {
     NC(g_nccl.AllReduce(loc, glob, (size_t)n, ncclDouble, ncclSum, c->comm, c->stream));
     return SM_OK;
@@ -356,7 +366,24 @@ static int dev_D(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, double m0,
 }
 
 // D D^dagger via the context's scratch field (the reference's global DTEMP, dirac_operator.cpp:477-480)
-// one-pass D D^dagger (sm_fused.cuh); single-tile lattices only (a split lattice would need 2-deep ghosts)
+// two boundary rows of a field (rows 0,1 to the -x neighbour, rows wx-2,wx-1 to the +x neighbour) into
+// the [comp][2][wt] ghost arrays; rows are contiguous in HBM, so nothing is packed
+static int exchange_rows2(sm_ctx* c, const cplx* field, cplx* lo_dst, cplx* hi_dst) {
+    const size_t n = 2 * (size_t)c->wt;   // complex per component
+    NC(g_nccl.GroupStart());
+    for (int comp = 0; comp < 2; comp++) {
+        const cplx* f = field + (size_t)comp * c->V;
+        NC(g_nccl.Send(f, 2 * n, ncclDouble, c->nb_xm, c->comm, c->stream));
+        NC(g_nccl.Send(f + (size_t)(c->wx - 2) * c->wt, 2 * n, ncclDouble, c->nb_xp, c->comm, c->stream));
+        NC(g_nccl.Recv(hi_dst + comp * n, 2 * n, ncclDouble, c->nb_xp, c->comm, c->stream));
+        NC(g_nccl.Recv(lo_dst + comp * n, 2 * n, ncclDouble, c->nb_xm, c->comm, c->stream));
+    }
+    NC(g_nccl.GroupEnd());
+    return SM_OK;
+}
+
+// one-pass D D^dagger (sm_fused.cuh): a single tile, or tiles split along x only (ranks_t == 1,
+// 2-row ghosts); a split along t keeps the two-pass kernels
 template <int MODE>
 static int launch_fused(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, double m0, double* sums_out = nullptr,
                         const cplx* r = nullptr, cplx* x = nullptr, cplx* d_new = nullptr, int k = 0) {
@@ -381,6 +408,27 @@ static int launch_fused(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, dou
     a.d_new = d_new;
     a.k = k;
     a.tol = c->tol;
+    if (c->dist()) {
+        if (c->f2_U_valid_for != U) {
+            TRY(exchange_rows2(c, U, c->f2_U[0], c->f2_U[1]));
+            c->f2_U_valid_for = U;
+        }
+        a.gU_lo = c->f2_U[0];
+        a.gU_hi = c->f2_U[1];
+        if (MODE == FUSED_CG) {
+            const int cur = k & 1;            // d_{k-1} ghosts were written by the previous pass
+            a.gin_lo = c->f2_d[cur ^ 1][0];
+            a.gin_hi = c->f2_d[cur ^ 1][1];
+            a.gd_lo = c->f2_d[cur][0];
+            a.gd_hi = c->f2_d[cur][1];
+            a.gr_lo = c->f2_r[0];             // exchanged by the caller after every residual update
+            a.gr_hi = c->f2_r[1];
+        } else {
+            TRY(exchange_rows2(c, in, c->f2_in[0], c->f2_in[1]));
+            a.gin_lo = c->f2_in[0];
+            a.gin_hi = c->f2_in[1];
+        }
+    }
     constexpr int STAGES = (MODE == FUSED_CG) ? 2 : 3;
     const size_t smem = fused_smem_bytes(MODE, STAGES, c->fus_block.x);
     static bool attr_set = false;   // per instantiation
@@ -394,7 +442,7 @@ static int launch_fused(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, dou
     return SM_OK;
 }
 
-static bool fused_ok(const sm_ctx* c) { return c->use_fused && !c->dist(); }
+static bool fused_ok(const sm_ctx* c) { return c->use_fused && (!c->dist() || (c->rt == 1 && c->wx >= 4)); }
 
 // D D^dagger: one pass over HBM on a single tile, else D^dagger then D through the context's
 // scratch field (the reference's global DTEMP, dirac_operator.cpp:477-480)
@@ -503,7 +551,10 @@ static int dev_cg_fused(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, doub
     c->launches++;
     // x = phi ; r = phi - D D^dagger phi ; |phi|^2, |r|^2   (d_0 = r_0 is formed by A(0))
     TRY((launch_wilson<true, WILSON_PLAIN>(c, U, phi, c->tmp, m0)));
-    TRY((launch_wilson<false, WILSON_CGINIT>(c, U, c->tmp, nullptr, m0, phi, c->cg_r, c->cg_d2, x, &st->phi_norm2)));
+    TRY((launch_wilson<false, WILSON_CGINIT>(c, U, c->tmp, nullptr, m0, phi, c->cg_r, c->cg_d2, x,
+                                             sum_target(c, &st->phi_norm2))));
+    TRY(sum_finish(c, &st->phi_norm2, 2));
+    if (c->dist()) TRY(exchange_rows2(c, c->cg_r, c->f2_r[0], c->f2_r[1]));
 
     const int batch = 8;
     int k = 0, slot = 0, prev = -1;
@@ -511,11 +562,16 @@ static int dev_cg_fused(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, doub
         const int k_end = std::min(max_iter, k + batch);
         for (; k < k_end; k++) {
             const int cur = k & 1;
-            TRY((launch_fused<FUSED_CG>(c, U, dbuf[cur ^ 1], c->cg_Ad, m0, st->dAd, c->cg_r, x, dbuf[cur], k)));
+            TRY((launch_fused<FUSED_CG>(c, U, dbuf[cur ^ 1], c->cg_Ad, m0, sum_target(c, st->dAd), c->cg_r, x,
+                                        dbuf[cur], k)));
+            TRY(sum_finish(c, st->dAd, 2));
             k_cg_resid<<<c->flat_blocks_c, kBlock, 0, c->stream>>>(st, cur, c->cg_r, c->cg_Ad, n_elems, c->partials,
-                                                                   c->tickets + TK_UPDATE, &st->rr[cur ^ 1]);
+                                                                   c->tickets + TK_UPDATE,
+                                                                   sum_target(c, &st->rr[cur ^ 1]));
             KCHECK();
             c->launches++;
+            TRY(sum_finish(c, &st->rr[cur ^ 1], 1));
+            if (c->dist()) TRY(exchange_rows2(c, c->cg_r, c->f2_r[0], c->f2_r[1]));
         }
         k_cg_check<<<1, 1, 0, c->stream>>>(st, k, tol, max_iter);
         KCHECK();
@@ -702,7 +758,7 @@ static int dev_leap_update(sm_ctx* c, cplx* U, double* pi, const double* F, doub
     k_leap_update<<<c->flat_blocks_c, kBlock, 0, c->stream>>>(U, pi, F, eps_pi, eps_u, 2 * c->V);
     KCHECK();
     c->launches++;
-    if (c->ghost_valid_for == U) c->ghost_valid_for = nullptr;
+    invalidate_gauge_ghosts(c, U);
     return SM_OK;
 }
 
@@ -710,6 +766,7 @@ static int dev_leap_update(sm_ctx* c, cplx* U, double* pi, const double* F, doub
 // host <-> device field copies (component arrays of the reference's spinor / re_field)
 // ------------------------------------------------------------------------------------------------
 static int h2d_c(sm_ctx* c, cplx* d, const double* h0, const double* h1) {
+    invalidate_gauge_ghosts(c, d);
     CU(cudaMemcpyAsync(d, h0, sizeof(cplx) * c->V, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(d + c->V, h1, sizeof(cplx) * c->V, cudaMemcpyHostToDevice, c->stream));
     return SM_OK;
@@ -796,7 +853,7 @@ static int hmc_leapfrog(sm_ctx* c, TrajAcc* acc) {
     const double eps = c->hp.trajectory_length / (md * 1.0);
     CU(cudaMemcpyAsync(c->pip, c->pi, sizeof(double) * 2 * c->V, cudaMemcpyDeviceToDevice, c->stream));
     CU(cudaMemcpyAsync(c->Up, c->U, sizeof(cplx) * 2 * c->V, cudaMemcpyDeviceToDevice, c->stream));
-    if (c->ghost_valid_for == c->Up) c->ghost_valid_for = nullptr;
+    invalidate_gauge_ghosts(c, c->Up);
     TRY(dev_leap_update(c, c->Up, c->pip, nullptr, 0.0, 0.5 * eps));
     TRY(hmc_force(c, c->Up, c->phi, c->F, acc));
     for (int step = 1; step < md - 1; step++) {
@@ -938,6 +995,15 @@ int sm_create_dist(int Nx, int Nt, int ranks_x, int ranks_t, int rank, int devic
         TRY(dev_alloc(&c->fg_t, 2 * wx));
         TRY(dev_alloc(&c->fg_x, 2 * wt));
         TRY(dev_alloc(&c->fg_send, 2 * wx + 2 * wt));
+        for (int side = 0; side < 2; side++) {
+            TRY(dev_alloc(&c->f2_U[side], 4 * wt));
+            TRY(dev_alloc(&c->f2_in[side], 4 * wt));
+            TRY(dev_alloc(&c->f2_r[side], 4 * wt));
+            TRY(dev_alloc(&c->f2_d[0][side], 4 * wt));
+            TRY(dev_alloc(&c->f2_d[1][side], 4 * wt));
+            CU(cudaMemsetAsync(c->f2_d[0][side], 0, sizeof(cplx) * 4 * wt, c->stream));
+            CU(cudaMemsetAsync(c->f2_d[1][side], 0, sizeof(cplx) * 4 * wt, c->stream));
+        }
         return SM_OK;
     };
     rc = body();
@@ -958,7 +1024,9 @@ int sm_destroy(sm_ctx* c) {
                     c->cg_Ad,    c->cg_d2, c->sU,      c->sA,      c->sB,      c->sC,       c->sF,      c->U,      c->Up,
                     c->chi,      c->phi,     c->psi,     c->xi,      c->pi,       c->pip,     c->F,      c->send_tm,
                     c->send_tp,  c->send_xm, c->send_xp, c->g_tp,    c->g_tm,     c->g_xp,    c->g_xm,   c->gg_xm,
-                    c->gg_xp,    c->gg_tm,   c->gg_tp,   c->gg_send, c->fg_t,     c->fg_x,    c->fg_send};
+                    c->gg_xp,    c->gg_tm,   c->gg_tp,   c->gg_send, c->fg_t,     c->fg_x,    c->fg_send,
+                    c->f2_U[0],  c->f2_U[1], c->f2_in[0], c->f2_in[1], c->f2_r[0], c->f2_r[1],
+                    c->f2_d[0][0], c->f2_d[0][1], c->f2_d[1][0], c->f2_d[1][1]};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (void* p : c->user_fields) cudaFree(p);
@@ -1103,7 +1171,7 @@ int sm_phi_dag_partialD_phi(sm_ctx* c, const double* U0, const double* U1, const
     TRY(h2d_c(c, c->sU, U0, U1));
     TRY(h2d_c(c, c->sA, l0, l1));
     TRY(h2d_c(c, c->sB, r0, r1));
-    c->ghost_valid_for = nullptr;
+    c->ghost_valid_for = c->f2_U_valid_for = nullptr;
     tick(c);
     TRY(dev_force(c, c->sU, c->sA, c->sB, c->sF, 0.0, true, false));
     TRY(tock(c));
@@ -1116,7 +1184,7 @@ int sm_compute_staple(sm_ctx* c, const double* U0, const double* U1, double* K0,
     NEED(U0); NEED(U1); NEED(K0); NEED(K1);
     TRY(ensure_staging(c));
     TRY(h2d_c(c, c->sU, U0, U1));
-    c->ghost_valid_for = nullptr;
+    c->ghost_valid_for = c->f2_U_valid_for = nullptr;
     tick(c);
     TRY(refresh_gauge_ghosts(c, c->sU));
     k_staple<<<c->flat_blocks_s, kBlock, 0, c->stream>>>(gauge_view(c, c->sU), c->sB);
@@ -1132,7 +1200,7 @@ int sm_compute_plaquette(sm_ctx* c, const double* U0, const double* U1, double b
     NEED(U0); NEED(U1); NEED(sums);
     TRY(ensure_staging(c));
     TRY(h2d_c(c, c->sU, U0, U1));
-    c->ghost_valid_for = nullptr;
+    c->ghost_valid_for = c->f2_U_valid_for = nullptr;
     tick(c);
     TRY(dev_plaquette(c, c->sU, beta, P ? c->sA : nullptr, c->sums));
     TRY(tock(c));
@@ -1169,7 +1237,7 @@ int sm_field_free(sm_ctx* c, double* d_field) {
 int sm_field_upload(sm_ctx* c, double* d, const double* h0, const double* h1, int complex_field) {
     TRY(set_device(c));
     NEED(d); NEED(h0); NEED(h1);
-    if (c->ghost_valid_for == (const cplx*)d) c->ghost_valid_for = nullptr;
+    invalidate_gauge_ghosts(c, (const cplx*)d);
     if (complex_field) TRY(h2d_c(c, (cplx*)d, h0, h1));
     else TRY(h2d_r(c, d, h0, h1));
     return sync(c);
@@ -1245,7 +1313,7 @@ int sm_hmc_set_gauge(sm_ctx* c, const double* U0, const double* U1) {
     TRY(set_device(c));
     NEED(U0); NEED(U1);
     TRY(hmc_alloc(c));
-    c->ghost_valid_for = nullptr;
+    c->ghost_valid_for = c->f2_U_valid_for = nullptr;
     TRY(h2d_c(c, c->U, U0, U1));
     c->hmc_has_gauge = true;
     return sync(c);
@@ -1339,7 +1407,7 @@ int sm_hmc_accept(sm_ctx* c, int accept) {
     if (!c->hmc_has_gauge) return fail(SM_ERR_STATE, "no gauge field set");
     if (accept) {   // GConf = GConf_copy (hmc.cpp:173) as a pointer swap
         std::swap(c->U, c->Up);
-        c->ghost_valid_for = nullptr;
+        c->ghost_valid_for = c->f2_U_valid_for = nullptr;
     }
     return SM_OK;
 }

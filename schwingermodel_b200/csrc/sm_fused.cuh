@@ -43,6 +43,16 @@ struct FusedArgs {
     cplx* d_new;         // d_k
     int k;
     double tol;
+    // lattice split along x (ranks_t == 1): rows -2,-1 ("lo") and wx, wx+1 ("hi") live in ghost
+    // arrays laid out [component][2 rows][wt]; null = wrap inside the tile
+    const cplx* gU_lo;
+    const cplx* gU_hi;
+    const cplx* gin_lo;   // ghost rows of `in`
+    const cplx* gin_hi;
+    const cplx* gr_lo;    // CG: ghost rows of r
+    const cplx* gr_hi;
+    cplx* gd_lo;          // CG: ghost rows of d_k, written here for the next iteration
+    cplx* gd_hi;
 };
 
 // hop algebra shared by both operators: s = +1 for D^dagger, -1 for D (see k_wilson)
@@ -133,22 +143,44 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_fused(const FusedArgs a) {
     }
 
     // stage row j: psi (or r, d_{k-1}, x) and the links of this thread's column
+    const bool split = (a.gU_lo != nullptr);
     auto issue_row = [&](int j) {
         if (col_active && j <= j_last) {
             double2* st = s_stage + ((j - j_first) % STAGES) * NARR * BT + tid;
-            const int n = wrap_idx(j, wx) * wt + t;
-            cp_async16(st + 0 * BT, a.U + n);
-            cp_async16(st + 1 * BT, a.U + V + n);
-            if (MODE != FUSED_CG) {
-                cp_async16(st + 2 * BT, a.in + n);
-                cp_async16(st + 3 * BT, a.in + V + n);
+            const cplx *pU, *pin, *pr = nullptr;
+            int cs;                                   // component stride of the source arrays
+            if (split && j < 0) {
+                const int o = (j + 2) * wt + t;
+                cs = 2 * wt;
+                pU = a.gU_lo + o;
+                pin = a.gin_lo + o;
+                if (MODE == FUSED_CG) pr = a.gr_lo + o;
+            } else if (split && j >= wx) {
+                const int o = (j - wx) * wt + t;
+                cs = 2 * wt;
+                pU = a.gU_hi + o;
+                pin = a.gin_hi + o;
+                if (MODE == FUSED_CG) pr = a.gr_hi + o;
             } else {
-                cp_async16(st + 2 * BT, a.r + n);
-                cp_async16(st + 3 * BT, a.r + V + n);
+                const int n = wrap_idx(j, wx) * wt + t;
+                cs = V;
+                pU = a.U + n;
+                pin = a.in + n;
+                if (MODE == FUSED_CG) pr = a.r + n;
+            }
+            cp_async16(st + 0 * BT, pU);
+            cp_async16(st + 1 * BT, pU + cs);
+            if (MODE != FUSED_CG) {
+                cp_async16(st + 2 * BT, pin);
+                cp_async16(st + 3 * BT, pin + cs);
+            } else {
+                cp_async16(st + 2 * BT, pr);
+                cp_async16(st + 3 * BT, pr + cs);
                 if (!first) {
-                    cp_async16(st + 4 * BT, a.in + n);
-                    cp_async16(st + 5 * BT, a.in + V + n);
+                    cp_async16(st + 4 * BT, pin);
+                    cp_async16(st + 5 * BT, pin + cs);
                     if (col_owner && j >= xa && j < xb) {
+                        const int n = j * wt + t;
                         cp_async16(st + 6 * BT, a.x + n);
                         cp_async16(st + 7 * BT, a.x + V + n);
                     }
@@ -184,10 +216,18 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_fused(const FusedArgs a) {
                 a.x[V + n] = cadd(st[7 * BT], cmul(alpha, d1));
             }
         }
-        if (MODE == FUSED_CG && col_owner && j >= xa && j < xb) {
-            const int n = j * wt + t;
-            a.d_new[n] = p0;
-            a.d_new[V + n] = p1;
+        if (MODE == FUSED_CG && col_owner) {
+            if (j >= xa && j < xb) {
+                const int n = j * wt + t;
+                a.d_new[n] = p0;
+                a.d_new[V + n] = p1;
+            } else if (split && j < 0) {             // keep d_k's ghost rows for the next iteration
+                a.gd_lo[(j + 2) * wt + t] = p0;
+                a.gd_lo[2 * wt + (j + 2) * wt + t] = p1;
+            } else if (split && j >= wx) {
+                a.gd_hi[(j - wx) * wt + t] = p0;
+                a.gd_hi[2 * wt + (j - wx) * wt + t] = p1;
+            }
         }
 
         // publish the t-direction half-spinors of psi row j-1 (for D^dagger) and t row j-2 (for D)

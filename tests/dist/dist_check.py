@@ -40,12 +40,18 @@ def main():
     F, _ = P.force(U, phi, beta, m0)
     tr = P.trajectory(U, pi, chi, md, tau, beta, m0)
     report = []
-    for rx, rt in decomps:
+    # every decomposition with the default path choice, and the x-only splits again with the one-pass
+    # D D^dagger forced (2-row ghosts), which small lattices would not pick on their own
+    cases = [(rx, rt, None) for rx, rt in decomps] + [(rx, rt, "onepass") for rx, rt in decomps if rt == 1 and rx > 1]
+    for rx, rt, path in cases:
+        if path:
+            os.environ["SM_DD_PATH"] = path
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             idt.copy_(torch.frombuffer(bytearray(sb.Lattice.nccl_unique_id()), dtype=torch.uint8))
         dist.broadcast(idt, 0)
         lat = sb.Lattice(nx, nt, device=local, ranks_x=rx, ranks_t=rt, rank=rank, nccl_id=idt.cpu().numpy().tobytes())
+        os.environ.pop("SM_DD_PATH", None)
         T = lambda f: tile_of(f, nx, nt, rx, rt, rank)   # noqa: E731
         tabs, otabs = lat.periodic_boundary(rx, rt, rank), P.tables(rx, rt, rank)
         assert all(np.array_equal(tabs[k], otabs[k]) for k in tabs)
@@ -90,7 +96,7 @@ def main():
         tol["U'"] = 1e-9
         tol["pi'"] = 1e-8
         bad = {k: v for k, v in e.items() if not v <= tol[k]}
-        report.append({"ranks_x": rx, "ranks_t": rt, "errors": e, "bad": bad})
+        report.append({"ranks_x": rx, "ranks_t": rt, "path": path or "default", "errors": e, "bad": bad})
         assert not bad, (rx, rt, bad)
         dist.barrier()
     if rank == 0:
