@@ -99,6 +99,9 @@ struct sm_ctx {
     int wx = 0, wt = 0, V = 0;
     int device = 0, sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t comm_stream = nullptr;   // halo exchanges that overlap the interior blocks
+    cudaEvent_t ev_ready = nullptr, ev_ghost = nullptr;
+    bool overlap = true;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_poll[2] = {nullptr, nullptr};
     double last_ms = 0.0;
     long long launches = 0;
@@ -108,6 +111,7 @@ struct sm_ctx {
     int rows_per_block = 0;
     dim3 fus_block, fus_grid;   // one-pass D D^dagger (sm_fused.cuh)
     int fus_rows = 0, fus_cols = 0;
+    int fus_rb = 8, fus_split_rows = 0, fus_split_chunks = 0;   // interior/boundary launch split (split lattice)
     bool use_fused = true;      // SM_DD_PATH=twopass selects the two-pass form
     int flat_blocks_c = 0;   // grid for flat passes over 2V elements
     int flat_blocks_s = 0;   // grid for passes over V sites
@@ -185,6 +189,10 @@ static int ctx_common_init(sm_ctx* c) {
                                      std::to_string(prop.major) + std::to_string(prop.minor));
     c->sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_ghost, cudaEventDisableTiming));
+    if (const char* e = getenv("SM_OVERLAP")) c->overlap = atoi(e) != 0;
     CU(cudaEventCreate(&c->ev_a));
     CU(cudaEventCreate(&c->ev_b));
     CU(cudaEventCreateWithFlags(&c->ev_poll[0], cudaEventDisableTiming));
@@ -215,15 +223,28 @@ static int ctx_common_init(sm_ctx* c) {
         const int strips = (c->wt + (BT - 4) - 1) / (BT - 4);
         c->fus_cols = (c->wt + strips - 1) / strips;     // equal strips
         const int capacity = c->sm_count * (BT == 128 ? 4 : 2);
-        int rows = (c->wx + std::max(1, 8 * capacity / strips) - 1) / std::max(1, 8 * capacity / strips);
-        if (rows < 64) {
-            const int chunks1 = std::max(1, capacity / strips);
-            rows = std::max(std::min(c->wx, 8), (c->wx + chunks1 - 1) / chunks1);
-        }
-        if (const char* r = getenv("SM_FUSED_ROWS")) rows = std::max(1, std::min(c->wx, atoi(r)));
+        auto rows_for = [&](int nrows) {
+            const int many = std::max(1, 8 * capacity / strips);
+            int rows = (nrows + many - 1) / many;
+            if (rows < 64) {
+                const int chunks1 = std::max(1, capacity / strips);
+                rows = std::max(std::min(nrows, 8), (nrows + chunks1 - 1) / chunks1);
+            }
+            if (const char* r = getenv("SM_FUSED_ROWS")) rows = std::max(1, std::min(nrows, atoi(r)));
+            return rows;
+        };
+        const int rows = rows_for(c->wx);
         c->fus_block = dim3(BT, 1, 1);
         c->fus_grid = dim3(strips, (c->wx + rows - 1) / rows, 1);
         c->fus_rows = rows;
+        // split lattice: two thin boundary bands (the only rows that read ghost rows) + interior chunks
+        c->fus_rb = 8;
+        c->fus_split_rows = c->fus_split_chunks = 0;
+        if (c->wx >= 4 * c->fus_rb) {
+            const int inner = c->wx - 2 * c->fus_rb;
+            c->fus_split_rows = rows_for(inner);
+            c->fus_split_chunks = (inner + c->fus_split_rows - 1) / c->fus_split_rows;
+        }
         long long min_sites = 1LL << 18;                 // below this the two-pass kernels win (one site per thread)
         if (const char* m = getenv("SM_FUSED_MIN_SITES")) min_sites = atoll(m);
         const char* e = getenv("SM_DD_PATH");
@@ -236,7 +257,7 @@ static int ctx_common_init(sm_ctx* c) {
     c->flat_blocks_s = std::max(1, std::min(cap, (c->V + kBlock - 1) / kBlock));
 
     const size_t max_blocks = std::max<size_t>(std::max<size_t>((size_t)nT * GY, (size_t)cap),
-                                               (size_t)c->fus_grid.x * c->fus_grid.y);
+                                               (size_t)c->fus_grid.x * (std::max<size_t>(c->fus_grid.y, c->fus_split_chunks) + 2));
     TRY(dev_alloc(&c->partials, max_blocks * kMaxSums));
     TRY(dev_alloc(&c->tickets, (size_t)TK_COUNT));
     CU(cudaMemsetAsync(c->tickets, 0, sizeof(unsigned int) * TK_COUNT, c->stream));
@@ -368,15 +389,16 @@ static int dev_D(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, double m0,
 // D D^dagger via the context's scratch field (the reference's global DTEMP, dirac_operator.cpp:477-480)
 // two boundary rows of a field (rows 0,1 to the -x neighbour, rows wx-2,wx-1 to the +x neighbour) into
 // the [comp][2][wt] ghost arrays; rows are contiguous in HBM, so nothing is packed
-static int exchange_rows2(sm_ctx* c, const cplx* field, cplx* lo_dst, cplx* hi_dst) {
+static int exchange_rows2(sm_ctx* c, const cplx* field, cplx* lo_dst, cplx* hi_dst, cudaStream_t st = nullptr) {
+    if (st == nullptr) st = c->stream;
     const size_t n = 2 * (size_t)c->wt;   // complex per component
     NC(g_nccl.GroupStart());
     for (int comp = 0; comp < 2; comp++) {
         const cplx* f = field + (size_t)comp * c->V;
-        NC(g_nccl.Send(f, 2 * n, ncclDouble, c->nb_xm, c->comm, c->stream));
-        NC(g_nccl.Send(f + (size_t)(c->wx - 2) * c->wt, 2 * n, ncclDouble, c->nb_xp, c->comm, c->stream));
-        NC(g_nccl.Recv(hi_dst + comp * n, 2 * n, ncclDouble, c->nb_xp, c->comm, c->stream));
-        NC(g_nccl.Recv(lo_dst + comp * n, 2 * n, ncclDouble, c->nb_xm, c->comm, c->stream));
+        NC(g_nccl.Send(f, 2 * n, ncclDouble, c->nb_xm, c->comm, st));
+        NC(g_nccl.Send(f + (size_t)(c->wx - 2) * c->wt, 2 * n, ncclDouble, c->nb_xp, c->comm, st));
+        NC(g_nccl.Recv(hi_dst + comp * n, 2 * n, ncclDouble, c->nb_xp, c->comm, st));
+        NC(g_nccl.Recv(lo_dst + comp * n, 2 * n, ncclDouble, c->nb_xm, c->comm, st));
     }
     NC(g_nccl.GroupEnd());
     return SM_OK;
@@ -408,27 +430,8 @@ static int launch_fused(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, dou
     a.d_new = d_new;
     a.k = k;
     a.tol = c->tol;
-    if (c->dist()) {
-        if (c->f2_U_valid_for != U) {
-            TRY(exchange_rows2(c, U, c->f2_U[0], c->f2_U[1]));
-            c->f2_U_valid_for = U;
-        }
-        a.gU_lo = c->f2_U[0];
-        a.gU_hi = c->f2_U[1];
-        if (MODE == FUSED_CG) {
-            const int cur = k & 1;            // d_{k-1} ghosts were written by the previous pass
-            a.gin_lo = c->f2_d[cur ^ 1][0];
-            a.gin_hi = c->f2_d[cur ^ 1][1];
-            a.gd_lo = c->f2_d[cur][0];
-            a.gd_hi = c->f2_d[cur][1];
-            a.gr_lo = c->f2_r[0];             // exchanged by the caller after every residual update
-            a.gr_hi = c->f2_r[1];
-        } else {
-            TRY(exchange_rows2(c, in, c->f2_in[0], c->f2_in[1]));
-            a.gin_lo = c->f2_in[0];
-            a.gin_hi = c->f2_in[1];
-        }
-    }
+    a.nchunks = c->fus_grid.y;
+    a.chunk_mode = 0;
     constexpr int STAGES = (MODE == FUSED_CG) ? 2 : 3;
     const size_t smem = fused_smem_bytes(MODE, STAGES, c->fus_block.x);
     static bool attr_set = false;   // per instantiation
@@ -436,9 +439,59 @@ static int launch_fused(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, dou
         CU(cudaFuncSetAttribute(k_dd_fused<MODE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
-    k_dd_fused<MODE, STAGES><<<c->fus_grid, c->fus_block, smem, c->stream>>>(a);
-    KCHECK();
-    c->launches++;
+    bool split_launch = false;
+    if (c->dist()) {
+        if (c->f2_U_valid_for != U) {
+            TRY(exchange_rows2(c, U, c->f2_U[0], c->f2_U[1]));
+            c->f2_U_valid_for = U;
+        }
+        a.gU_lo = c->f2_U[0];
+        a.gU_hi = c->f2_U[1];
+        // the ghost rows this pass needs: psi (PLAIN) or r (CG; d_{k-1} ghosts were written by the previous pass).
+        // Only the first and last row chunk read them, so the exchange runs on the comm stream while
+        // the interior chunks compute.
+        const cplx* moving = (MODE == FUSED_CG) ? r : in;
+        cplx** dst = (MODE == FUSED_CG) ? c->f2_r : c->f2_in;
+        split_launch = c->overlap && c->fus_split_chunks >= 1;
+        if (split_launch) {
+            CU(cudaEventRecord(c->ev_ready, c->stream));
+            CU(cudaStreamWaitEvent(c->comm_stream, c->ev_ready, 0));
+            TRY(exchange_rows2(c, moving, dst[0], dst[1], c->comm_stream));
+        } else {
+            TRY(exchange_rows2(c, moving, dst[0], dst[1]));
+        }
+        if (MODE == FUSED_CG) {
+            const int cur = k & 1;
+            a.gin_lo = c->f2_d[cur ^ 1][0];
+            a.gin_hi = c->f2_d[cur ^ 1][1];
+            a.gd_lo = c->f2_d[cur][0];
+            a.gd_hi = c->f2_d[cur][1];
+            a.gr_lo = c->f2_r[0];
+            a.gr_hi = c->f2_r[1];
+        } else {
+            a.gin_lo = c->f2_in[0];
+            a.gin_hi = c->f2_in[1];
+        }
+    }
+    if (split_launch) {
+        // boundary bands follow the exchange on the comm stream; the interior runs meanwhile
+        a.rb = c->fus_rb;
+        a.rows_per_block = c->fus_split_rows;
+        a.nchunks = c->fus_split_chunks + 2;
+        a.chunk_mode = 2;
+        k_dd_fused<MODE, STAGES><<<dim3(c->fus_grid.x, 2, 1), c->fus_block, smem, c->comm_stream>>>(a);
+        KCHECK();
+        CU(cudaEventRecord(c->ev_ghost, c->comm_stream));
+        a.chunk_mode = 1;
+        k_dd_fused<MODE, STAGES><<<dim3(c->fus_grid.x, c->fus_split_chunks, 1), c->fus_block, smem, c->stream>>>(a);
+        KCHECK();
+        CU(cudaStreamWaitEvent(c->stream, c->ev_ghost, 0));
+        c->launches += 2;
+    } else {
+        k_dd_fused<MODE, STAGES><<<c->fus_grid, c->fus_block, smem, c->stream>>>(a);
+        KCHECK();
+        c->launches++;
+    }
     return SM_OK;
 }
 
@@ -554,7 +607,6 @@ static int dev_cg_fused(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, doub
     TRY((launch_wilson<false, WILSON_CGINIT>(c, U, c->tmp, nullptr, m0, phi, c->cg_r, c->cg_d2, x,
                                              sum_target(c, &st->phi_norm2))));
     TRY(sum_finish(c, &st->phi_norm2, 2));
-    if (c->dist()) TRY(exchange_rows2(c, c->cg_r, c->f2_r[0], c->f2_r[1]));
 
     const int batch = 8;
     int k = 0, slot = 0, prev = -1;
@@ -571,7 +623,6 @@ static int dev_cg_fused(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, doub
             KCHECK();
             c->launches++;
             TRY(sum_finish(c, &st->rr[cur ^ 1], 1));
-            if (c->dist()) TRY(exchange_rows2(c, c->cg_r, c->f2_r[0], c->f2_r[1]));
         }
         k_cg_check<<<1, 1, 0, c->stream>>>(st, k, tol, max_iter);
         KCHECK();
@@ -1036,6 +1087,9 @@ int sm_destroy(sm_ctx* c) {
     cudaEventDestroy(c->ev_poll[0]);
     cudaEventDestroy(c->ev_poll[1]);
     cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->comm_stream);
+    cudaEventDestroy(c->ev_ready);
+    cudaEventDestroy(c->ev_ghost);
     delete c;
     return SM_OK;
 }

@@ -50,16 +50,21 @@ __device__ __forceinline__ double warp_sum(double v) {
 //      result[j].  Blocks/partials are bounded by the persistent grid (a few thousand at most).
 // Returns true in ALL threads of the finishing block (result[] is then valid in thread 0 only
 // through the returned values in `v`).
+// A reduction may span several launches (interior + boundary blocks of one pass): they share the
+// ticket, and pass the total block count and their global block index explicitly.
 template <int NS>
-__device__ __forceinline__ bool grid_reduce(double (&v)[NS], double* __restrict__ partials, unsigned int* ticket) {
+__device__ __forceinline__ bool grid_reduce(double (&v)[NS], double* __restrict__ partials, unsigned int* ticket,
+                                            int nblocks = -1, int bid = -1) {
     __shared__ double s_part[kWarps][NS];
     __shared__ bool s_last;
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     const int nthreads = blockDim.x * blockDim.y;      // a multiple of 32, at most kBlock
     const int nwarps = nthreads >> 5;
     const int lane = tid & 31, warp = tid >> 5;
-    const int nblocks = gridDim.x * gridDim.y;
-    const int bid = blockIdx.y * gridDim.x + blockIdx.x;
+    if (nblocks < 0) {
+        nblocks = gridDim.x * gridDim.y;
+        bid = blockIdx.y * gridDim.x + blockIdx.x;
+    }
 #pragma unroll
     for (int j = 0; j < NS; j++) v[j] = warp_sum(v[j]);
     if (lane == 0) {

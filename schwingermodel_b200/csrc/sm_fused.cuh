@@ -31,6 +31,9 @@ struct FusedArgs {
     int wx, wt, V;
     int rows_per_block;
     int cols_per_strip;  // output columns per block (<= blockDim.x - 4)
+    int nchunks;         // row chunks of the whole pass (for the reduction that spans its launches)
+    int chunk_mode;      // 0: all rows, uniform chunks; 1: interior rows [rb, wx-rb); 2: the two boundary bands
+    int rb;              // rows per boundary band (split lattice; the only rows that read ghost rows)
     double mass;
     double sR_edge, sL_edge;
     double* partials;
@@ -132,8 +135,20 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_fused(const FusedArgs a) {
     const bool col_owner = (tid >= 2) && (tid < a.cols_per_strip + 2) && (tc < wt);
     const double sR = (t == wt - 1) ? a.sR_edge : 1.0;
     const double sL = (t == 0) ? a.sL_edge : 1.0;
-    const int xa = blockIdx.y * a.rows_per_block;
-    const int xb = min(wx, xa + a.rows_per_block);
+    int chunk, xa, xb;
+    if (a.chunk_mode == 0) {
+        chunk = blockIdx.y;
+        xa = chunk * a.rows_per_block;
+        xb = min(wx, xa + a.rows_per_block);
+    } else if (a.chunk_mode == 1) {
+        chunk = blockIdx.y + 1;
+        xa = a.rb + (int)blockIdx.y * a.rows_per_block;
+        xb = min(wx - a.rb, xa + a.rows_per_block);
+    } else {
+        chunk = (blockIdx.y == 0) ? 0 : a.nchunks - 1;
+        xa = (blockIdx.y == 0) ? 0 : wx - a.rb;
+        xb = xa + a.rb;
+    }
     const int tl = (tid == 0) ? 0 : tid - 1, tr = (tid == BT - 1) ? tid : tid + 1;
     const int j_first = xa - 2, j_last = xb + 1;
 
@@ -275,7 +290,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_fused(const FusedArgs a) {
     }
 
     if (MODE != FUSED_PLAIN) {
-        if (grid_reduce<2>(acc, a.partials, a.ticket)) {
+        if (grid_reduce<2>(acc, a.partials, a.ticket, (int)gridDim.x * a.nchunks, chunk * (int)gridDim.x + (int)blockIdx.x)) {
             if (tid == 0) {
                 a.sums_out[0] = acc[0];
                 a.sums_out[1] = acc[1];

@@ -27,7 +27,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     decomps = [(rx, world // rx) for rx in range(1, world + 1) if world % rx == 0]
-    nx, nt, m0, beta, md, tau = 32, 48, -0.05, 2.0, 5, 0.5
+    nx, nt, m0, beta, md, tau = 64, 48, -0.05, 2.0, 5, 0.5
     P = Port(nx, nt)
     U = P.hot_start(12345)
     chi, pi = gaussian_fields(nx, nt, 777)
