@@ -218,20 +218,26 @@ static int ctx_common_init(sm_ctx* c) {
     // blocks with >= 64 rows each (4 warm-up rows per chunk); mid-size: one resident wave.
     {
         const long long V = (long long)c->wx * c->wt;
-        int BT = (c->wt + 4 <= 128 || V <= (1LL << 22)) ? 128 : 256;
+        int BT = (c->wt + 4 <= 128 || V <= (1LL << 21)) ? 128 : 256;
         if (const char* e = getenv("SM_FUSED_BT")) BT = atoi(e) == 128 ? 128 : 256;
         const int strips = (c->wt + (BT - 4) - 1) / (BT - 4);
         c->fus_cols = (c->wt + strips - 1) / strips;     // equal strips
         const int capacity = c->sm_count * (BT == 128 ? 4 : 2);
+        // rows per chunk: minimise  waves x (rows + 4 warm-up rows)  with waves = ceil(blocks / resident blocks);
+        // this model reproduces the measured sweep (profiles/r01_sweep_rows.txt) to a few per cent
         auto rows_for = [&](int nrows) {
-            const int many = std::max(1, 8 * capacity / strips);
-            int rows = (nrows + many - 1) / many;
-            if (rows < 64) {
-                const int chunks1 = std::max(1, capacity / strips);
-                rows = std::max(std::min(nrows, 8), (nrows + chunks1 - 1) / chunks1);
+            if (const char* r = getenv("SM_FUSED_ROWS")) return std::max(1, std::min(nrows, atoi(r)));
+            int best = std::min(nrows, 8);
+            long long best_cost = -1;
+            for (int r = std::min(nrows, 8); r <= std::min(nrows, 512); r++) {
+                const long long blocks = (long long)strips * ((nrows + r - 1) / r);
+                const long long cost = ((blocks + capacity - 1) / capacity) * (r + 4);
+                if (best_cost < 0 || cost <= best_cost) {
+                    best_cost = cost;
+                    best = r;
+                }
             }
-            if (const char* r = getenv("SM_FUSED_ROWS")) rows = std::max(1, std::min(nrows, atoi(r)));
-            return rows;
+            return best;
         };
         const int rows = rows_for(c->wx);
         c->fus_block = dim3(BT, 1, 1);
