@@ -16,6 +16,7 @@
 
 #include "sm_kernels.cuh"
 #include "sm_fused.cuh"
+#include "sm_cluster_cg.cuh"
 
 using namespace sm;
 
@@ -154,6 +155,18 @@ struct sm_ctx {
 
     std::vector<void*> user_fields;
 
+    // CUDA graphs of one batch of one-pass CG iterations, keyed on what the kernels bake in
+    struct CgGraph {
+        const cplx* U;
+        cplx* x;
+        double m0, tol;
+        cudaGraphExec_t exec;
+        int kernels;
+    };
+    std::vector<CgGraph> cg_graphs;
+    bool use_graphs = true;
+    bool use_cluster = true;   // whole-solve cluster kernel for lattices of <= 4096 sites (SM_CLUSTER_CG=0 disables)
+
     bool dist() const { return nranks > 1; }
     double sR_edge() const { return (ct == rt - 1) ? -1.0 : 1.0; }
     double sL_edge() const { return (ct == 0) ? -1.0 : 1.0; }
@@ -193,6 +206,8 @@ static int ctx_common_init(sm_ctx* c) {
     CU(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_ghost, cudaEventDisableTiming));
     if (const char* e = getenv("SM_OVERLAP")) c->overlap = atoi(e) != 0;
+    if (const char* e = getenv("SM_GRAPHS")) c->use_graphs = atoi(e) != 0;
+    if (const char* e = getenv("SM_CLUSTER_CG")) c->use_cluster = atoi(e) != 0;
     CU(cudaEventCreate(&c->ev_a));
     CU(cudaEventCreate(&c->ev_b));
     CU(cudaEventCreateWithFlags(&c->ev_poll[0], cudaEventDisableTiming));
@@ -251,7 +266,7 @@ static int ctx_common_init(sm_ctx* c) {
             c->fus_split_rows = rows_for(inner);
             c->fus_split_chunks = (inner + c->fus_split_rows - 1) / c->fus_split_rows;
         }
-        long long min_sites = 1LL << 18;                 // below this the two-pass kernels win (one site per thread)
+        long long min_sites = 0;                         // measured: never slower than two passes (profiles/r01_sweep_sizes_*)
         if (const char* m = getenv("SM_FUSED_MIN_SITES")) min_sites = atoll(m);
         const char* e = getenv("SM_DD_PATH");
         c->use_fused = !(e && std::string(e) == "twopass") && V >= min_sites;
@@ -434,7 +449,8 @@ static int launch_fused(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, dou
     a.r = r;
     a.x = x;
     a.d_new = d_new;
-    a.k = k;
+    a.first = (k == 0);
+    a.cur = k & 1;
     a.tol = c->tol;
     a.nchunks = c->fus_grid.y;
     a.chunk_mode = 0;
@@ -614,25 +630,68 @@ static int dev_cg_fused(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, doub
                                              sum_target(c, &st->phi_norm2))));
     TRY(sum_finish(c, &st->phi_norm2, 2));
 
-    const int batch = 8;
-    int k = 0, slot = 0, prev = -1;
-    for (;;) {
-        const int k_end = std::min(max_iter, k + batch);
-        for (; k < k_end; k++) {
-            const int cur = k & 1;
-            TRY((launch_fused<FUSED_CG>(c, U, dbuf[cur ^ 1], c->cg_Ad, m0, sum_target(c, st->dAd), c->cg_r, x,
-                                        dbuf[cur], k)));
-            TRY(sum_finish(c, st->dAd, 2));
-            k_cg_resid<<<c->flat_blocks_c, kBlock, 0, c->stream>>>(st, cur, c->cg_r, c->cg_Ad, n_elems, c->partials,
-                                                                   c->tickets + TK_UPDATE,
-                                                                   sum_target(c, &st->rr[cur ^ 1]));
-            KCHECK();
-            c->launches++;
-            TRY(sum_finish(c, &st->rr[cur ^ 1], 1));
-        }
-        k_cg_check<<<1, 1, 0, c->stream>>>(st, k, tol, max_iter);
+    // one iteration: A(k) then B(k) (+ the all-reduces of their sums on a split lattice)
+    auto iteration = [&](int k) -> int {
+        const int cur = k & 1;
+        TRY((launch_fused<FUSED_CG>(c, U, dbuf[cur ^ 1], c->cg_Ad, m0, sum_target(c, st->dAd), c->cg_r, x, dbuf[cur], k)));
+        TRY(sum_finish(c, st->dAd, 2));
+        k_cg_resid<<<c->flat_blocks_c, kBlock, 0, c->stream>>>(st, cur, c->cg_r, c->cg_Ad, n_elems, c->partials,
+                                                               c->tickets + TK_UPDATE, sum_target(c, &st->rr[cur ^ 1]));
         KCHECK();
         c->launches++;
+        return sum_finish(c, &st->rr[cur ^ 1], 1);
+    };
+    const int batch = 8;   // even: a replayed batch always starts on the same parity
+
+    // a batch of iterations k = 1 + 8 m ... as one CUDA graph (single tile; the iteration index lives in
+    // CgState::k, so the nodes are iteration-independent)
+    cudaGraphExec_t exec = nullptr;
+    int graph_kernels = 0;
+    if (c->use_graphs && !c->dist() && max_iter > batch) {
+        for (auto& g : c->cg_graphs)
+            if (g.U == U && g.x == x && g.m0 == m0 && g.tol == tol) {
+                exec = g.exec;
+                graph_kernels = g.kernels;
+            }
+    }
+
+    int k = 0, slot = 0, prev = -1;
+    TRY(iteration(k++));   // k = 0 is special (d_0 = r_0) and also sets the kernel attributes before any capture
+    if (c->use_graphs && !c->dist() && max_iter > batch && exec == nullptr) {
+        const long long l0 = c->launches;
+        cudaGraph_t graph = nullptr;
+        CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = SM_OK;
+        for (int i = 0; i < batch && rc == SM_OK; i++) rc = iteration(1 + i);
+        if (rc == SM_OK) {
+            k_cg_check_dev<<<1, 1, 0, c->stream>>>(st, tol, max_iter);
+            c->launches++;
+        }
+        cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+        if (rc != SM_OK) return rc;
+        if (e != cudaSuccess) return fail(SM_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+        graph_kernels = (int)(c->launches - l0);
+        c->launches = l0;
+        CU(cudaGraphInstantiate(&exec, graph, 0));
+        cudaGraphDestroy(graph);
+        if (c->cg_graphs.size() >= 16) {
+            cudaGraphExecDestroy(c->cg_graphs.front().exec);
+            c->cg_graphs.erase(c->cg_graphs.begin());
+        }
+        c->cg_graphs.push_back({U, x, m0, tol, exec, graph_kernels});
+    }
+    for (;;) {
+        if (exec != nullptr && k + batch <= max_iter) {
+            CU(cudaGraphLaunch(exec, c->stream));
+            c->launches += graph_kernels;
+            k += batch;
+        } else {
+            const int k_end = std::min(max_iter, k + batch);
+            for (; k < k_end; k++) TRY(iteration(k));
+            k_cg_check_dev<<<1, 1, 0, c->stream>>>(st, tol, max_iter);
+            KCHECK();
+            c->launches++;
+        }
         CU(cudaMemcpyAsync(&c->h->cg[slot], st, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
         CU(cudaEventRecord(c->ev_poll[slot], c->stream));
         if (prev >= 0) {
@@ -653,7 +712,52 @@ static int dev_cg_fused(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, doub
     return SM_OK;
 }
 
+// small lattices: the whole solve in one launch of one thread-block cluster (sm_cluster_cg.cuh)
+static int dev_cg_cluster(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, int* converged, int* iterations) {
+    ClusterCgArgs a{};
+    a.U = U;
+    a.phi = phi;
+    a.x = x;
+    a.wx = c->wx;
+    a.wt = c->wt;
+    a.V = c->V;
+    a.mass = m0 + 2;
+    a.sR_edge = c->sR_edge();
+    a.sL_edge = c->sL_edge();
+    a.tol = c->tol;
+    a.max_iter = c->max_iter;
+    a.st = c->cg;
+    int ctas = 1;
+    while (ctas * kClusterThreads < c->V) ctas *= 2;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(k_cg_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas, 1, 1);
+    cfg.blockDim = dim3(kClusterThreads, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = ctas;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CU(cudaLaunchKernelEx(&cfg, k_cg_cluster, a));
+    c->launches++;
+    CU(cudaMemcpyAsync(&c->h->cg[0], c->cg, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (converged) *converged = c->h->cg[0].converged;
+    if (iterations) *iterations = c->h->cg[0].iters;
+    return SM_OK;
+}
+
 static int dev_cg(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, int* converged, int* iterations) {
+    if (c->use_cluster && !c->dist() && c->V <= kClusterMaxCtas * kClusterThreads)
+        return dev_cg_cluster(c, U, phi, x, m0, converged, iterations);
     if (fused_ok(c)) return dev_cg_fused(c, U, phi, x, m0, converged, iterations);
     return dev_cg_twopass(c, U, phi, x, m0, converged, iterations);
 }
@@ -1087,6 +1191,7 @@ int sm_destroy(sm_ctx* c) {
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (void* p : c->user_fields) cudaFree(p);
+    for (auto& g : c->cg_graphs) cudaGraphExecDestroy(g.exec);
     if (c->h) cudaFreeHost(c->h);
     cudaEventDestroy(c->ev_a);
     cudaEventDestroy(c->ev_b);

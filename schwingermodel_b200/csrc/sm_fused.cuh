@@ -44,7 +44,8 @@ struct FusedArgs {
     const cplx* r;       // r_k
     cplx* x;             // x_{k-1} -> x_k
     cplx* d_new;         // d_k
-    int k;
+    int first;           // iteration 0: d_0 = r_0, no x update owed
+    int cur;             // parity of the iteration (selects rr[], the d ping-pong is in the pointers)
     double tol;
     // lattice split along x (ranks_t == 1): rows -2,-1 ("lo") and wx, wx+1 ("hi") live in ghost
     // arrays laid out [component][2 rows][wt]; null = wrap inside the tile
@@ -113,12 +114,12 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_fused(const FusedArgs a) {
     bool first = true;
     if (MODE == FUSED_CG) {
         if (a.st->done) return;
-        const int cur = a.k & 1;
-        first = (a.k == 0);
+        const int cur = a.cur;
+        first = (a.first != 0);
         if (!first) {
             if (cg_converged(a.st, cur, a.tol)) {
-                if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
-                    a.st->iters = a.k - 1;
+                if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0 && a.chunk_mode != 1) {
+                    a.st->iters = a.st->k - 1;
                     a.st->converged = 1;
                     a.st->done = 1;
                 }
@@ -321,6 +322,7 @@ __global__ void __launch_bounds__(kBlock) k_cg_resid(CgState* st, int cur, cplx*
             st->alpha[1] = alpha.y;
             st->pending = 1;        // x still lacks alpha_k d_k
             st->pending_buf = cur;  // d_k lives in d buffer (k & 1)
+            st->k = st->k + 1;
         }
     }
 }

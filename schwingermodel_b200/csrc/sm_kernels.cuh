@@ -59,7 +59,7 @@ struct CgState {
     int converged;      // the reference's return value
     int pending;        // fused path: an x update is owed
     int pending_buf;    // ... with d in ping-pong buffer 0/1
-    int pad;
+    int k;              // iteration counter kept on the device (one-pass path: kernels are replayed from a CUDA graph)
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -356,12 +356,28 @@ __global__ void k_cg_check(CgState* st, int k, double tol, int max_iter) {
     }
 }
 
+// the same with the device-side iteration counter (one-pass path)
+__global__ void k_cg_check_dev(CgState* st, double tol, int max_iter) {
+    if (st->done) return;
+    const int k = st->k;
+    if (cg_converged(st, k & 1, tol)) {
+        st->iters = k - 1;
+        st->converged = 1;
+        st->done = 1;
+    } else if (k >= max_iter) {
+        st->iters = max_iter;
+        st->converged = 0;
+        st->done = 1;
+    }
+}
+
 __global__ void k_cg_reset(CgState* st) {
     st->done = 0;
     st->iters = 0;
     st->converged = 0;
     st->pending = 0;
     st->pending_buf = 0;
+    st->k = 0;
 }
 
 // dot(x,y) = sum x conj(y) over both components (include/variables.h:181-192)

@@ -371,3 +371,34 @@ def test_one_pass_and_two_pass_DDdag_agree(sb):
             tiny.close()
         one.close()
         two.close()
+
+
+def test_cg_execution_strategies_agree(sb):
+    """Cluster-resident CG (<= 4096 sites), CUDA-graph batches and plain launches run the same algorithm."""
+    from oracle.port import Port, gaussian_fields
+    for nx, nt, m0 in [(64, 64, 0.0), (16, 24, -0.05), (48, 80, 0.02), (5, 7, 0.3)]:
+        P = Port(nx, nt)
+        U = P.hot_start(5)
+        phi, _ = gaussian_fields(nx, nt, 6)
+        xo, oko, apps, _ = P.cg(U, phi, m0)
+        got = {}
+        for name, env in [("cluster", {}), ("graphs", {"SM_CLUSTER_CG": "0"}),
+                          ("launches", {"SM_CLUSTER_CG": "0", "SM_GRAPHS": "0"}),
+                          ("twopass", {"SM_CLUSTER_CG": "0", "SM_DD_PATH": "twopass"})]:
+            os.environ.update(env)
+            lat = sb.Lattice(nx, nt)
+            for k in env:
+                os.environ.pop(k)
+            x, ok, its = lat.conjugate_gradient(U, phi, m0)
+            x2, ok2, its2 = lat.conjugate_gradient(U, phi, m0)        # second solve replays the cached graph
+            assert (ok, its) == (ok2, its2) and np.array_equal(x, x2), name
+            assert ok == oko == 1 and abs(its + 2 - apps) <= 1, (name, its, apps)
+            assert relerr(x, xo) <= TOL_X, name
+            lat.set_cg(1e-10, 11)                                      # stop mid-way: same iterate everywhere
+            xm, okm, itm = lat.conjugate_gradient(U, phi, m0)
+            assert okm == 0 and itm == 11
+            got[name] = xm
+            lat.close()
+        xref = P.cg(U, phi, m0, 1e-10, 11)[0]
+        for name, xm in got.items():
+            assert relerr(xm, xref) <= 1e-10, name
