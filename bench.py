@@ -305,17 +305,17 @@ def run_b200(args):
     keepP, phi_p = pinned_like(phi_h)
     keepX, x_p = pinned_like(phi_h)
     lat.set_cg(1e-10, 10000)
-    e2e_steps = max(1, min(args.e2e_steps, args.steps))
-    if args.warmup > 0:
+    e2e_steps = max(0, min(args.e2e_steps, args.steps))
+    if args.warmup > 0 and e2e_steps > 0:
         _cg_into(lat, U_p, phi_p, x_p, m0)      # one untimed solve
     barrier()
     t0 = time.perf_counter()
-    apps = 0
+    apps, ok = 0, -1
     for _ in range(e2e_steps):
         x, ok, its = _cg_into(lat, U_p, phi_p, x_p, m0)
         apps += its + 2
     barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_s = max(max_over_ranks(time.perf_counter() - t0), 1e-9)
     e2e = {"value": apps * (L * L) / e2e_s, "unit": UNIT,
            "h2d_bytes_per_step": int(N * 2 * U_p.nbytes), "d2h_bytes_per_step": int(N * x_p.nbytes),
            "call": "sm_conjugate_gradient (host buffers)", "solves": e2e_steps, "dd_applications": apps,

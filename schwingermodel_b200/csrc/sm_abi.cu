@@ -202,7 +202,11 @@ static int ctx_common_init(sm_ctx* c) {
                                      std::to_string(prop.major) + std::to_string(prop.minor));
     c->sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;   // the comm stream outranks the compute stream: its few blocks go first when slots free up
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, hi));
+    }
     CU(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_ghost, cudaEventDisableTiming));
     if (const char* e = getenv("SM_OVERLAP")) c->overlap = atoi(e) != 0;
@@ -260,10 +264,12 @@ static int ctx_common_init(sm_ctx* c) {
         c->fus_rows = rows;
         // split lattice: two thin boundary bands (the only rows that read ghost rows) + interior chunks
         c->fus_rb = 8;
+        if (const char* r = getenv("SM_FUSED_RB")) c->fus_rb = std::max(2, atoi(r));
         c->fus_split_rows = c->fus_split_chunks = 0;
         if (c->wx >= 4 * c->fus_rb) {
             const int inner = c->wx - 2 * c->fus_rb;
             c->fus_split_rows = rows_for(inner);
+            if (const char* r = getenv("SM_FUSED_SPLIT_ROWS")) c->fus_split_rows = std::max(1, std::min(inner, atoi(r)));
             c->fus_split_chunks = (inner + c->fus_split_rows - 1) / c->fus_split_rows;
         }
         long long min_sites = 0;                         // measured: never slower than two passes (profiles/r01_sweep_sizes_*)
