@@ -165,7 +165,10 @@ struct sm_ctx {
     };
     std::vector<CgGraph> cg_graphs;
     bool use_graphs = true;
-    bool use_cluster = true;   // whole-solve cluster kernel for lattices of <= 4096 sites (SM_CLUSTER_CG=0 disables)
+    bool use_cluster = true;   // whole-solve resident kernels for small lattices (SM_CLUSTER_CG=0 disables)
+    int coop_sites = -1;
+    cplx* coop_hop = nullptr;
+    double* coop_wsum = nullptr;
 
     bool dist() const { return nranks > 1; }
     double sR_edge() const { return (ct == rt - 1) ? -1.0 : 1.0; }
@@ -718,21 +721,37 @@ static int dev_cg_fused(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, doub
     return SM_OK;
 }
 
-// small lattices: the whole solve in one launch of one thread-block cluster (sm_cluster_cg.cuh)
+// small lattices: the whole solve in one launch, every site resident in one thread (sm_cluster_cg.cuh):
+// one thread-block cluster up to 4096 sites, a cooperative grid up to one 512-thread CTA per SM
+static int resident_args(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, ResidentCgArgs* a) {
+    *a = ResidentCgArgs{};
+    a->U = U;
+    a->phi = phi;
+    a->x = x;
+    a->wx = c->wx;
+    a->wt = c->wt;
+    a->V = c->V;
+    a->mass = m0 + 2;
+    a->sR_edge = c->sR_edge();
+    a->sL_edge = c->sL_edge();
+    a->tol = c->tol;
+    a->max_iter = c->max_iter;
+    a->st = c->cg;
+    return SM_OK;
+}
+
+static int resident_finish(sm_ctx* c, int* converged, int* iterations) {
+    c->launches++;
+    CU(cudaMemcpyAsync(&c->h->cg[0], c->cg, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (converged) *converged = c->h->cg[0].converged;
+    if (iterations) *iterations = c->h->cg[0].iters;
+    return SM_OK;
+}
+
 static int dev_cg_cluster(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, int* converged, int* iterations) {
-    ClusterCgArgs a{};
-    a.U = U;
-    a.phi = phi;
-    a.x = x;
-    a.wx = c->wx;
-    a.wt = c->wt;
-    a.V = c->V;
-    a.mass = m0 + 2;
-    a.sR_edge = c->sR_edge();
-    a.sL_edge = c->sL_edge();
-    a.tol = c->tol;
-    a.max_iter = c->max_iter;
-    a.st = c->cg;
+    ResidentCgArgs a;
+    TRY(resident_args(c, U, phi, x, m0, &a));
     int ctas = 1;
     while (ctas * kClusterThreads < c->V) ctas *= 2;
     static bool attr_set = false;
@@ -753,17 +772,42 @@ static int dev_cg_cluster(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, do
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     CU(cudaLaunchKernelEx(&cfg, k_cg_cluster, a));
-    c->launches++;
-    CU(cudaMemcpyAsync(&c->h->cg[0], c->cg, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    if (converged) *converged = c->h->cg[0].converged;
-    if (iterations) *iterations = c->h->cg[0].iters;
-    return SM_OK;
+    return resident_finish(c, converged, iterations);
+}
+
+// how many sites the cooperative-grid solve can hold on this device (0: not available)
+static int coop_capacity(sm_ctx* c) {
+    if (c->coop_sites < 0) {
+        int per_sm = 0, coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
+        if (!coop || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_coop, kCoopThreads, 0) != cudaSuccess)
+            per_sm = 0;
+        c->coop_sites = per_sm * c->sm_count * kCoopThreads;
+    }
+    return c->coop_sites;
+}
+
+static int dev_cg_coop(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, int* converged, int* iterations) {
+    ResidentCgArgs a;
+    TRY(resident_args(c, U, phi, x, m0, &a));
+    const int blocks = (c->V + kCoopThreads - 1) / kCoopThreads;
+    if (!c->coop_hop) {
+        TRY(dev_alloc(&c->coop_hop, (size_t)8 * c->V));
+        TRY(dev_alloc(&c->coop_wsum, (size_t)4 * blocks * (kCoopThreads / 32)));
+    }
+    a.hop = c->coop_hop;
+    a.wsum = c->coop_wsum;
+    void* params[] = {&a};
+    CU(cudaLaunchCooperativeKernel((const void*)k_cg_coop, dim3(blocks, 1, 1), dim3(kCoopThreads, 1, 1), params, 0,
+                                   c->stream));
+    return resident_finish(c, converged, iterations);
 }
 
 static int dev_cg(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, int* converged, int* iterations) {
-    if (c->use_cluster && !c->dist() && c->V <= kClusterMaxCtas * kClusterThreads)
-        return dev_cg_cluster(c, U, phi, x, m0, converged, iterations);
+    if (c->use_cluster && !c->dist()) {
+        if (c->V <= kClusterMaxCtas * kClusterThreads) return dev_cg_cluster(c, U, phi, x, m0, converged, iterations);
+        if (c->V <= coop_capacity(c)) return dev_cg_coop(c, U, phi, x, m0, converged, iterations);
+    }
     if (fused_ok(c)) return dev_cg_fused(c, U, phi, x, m0, converged, iterations);
     return dev_cg_twopass(c, U, phi, x, m0, converged, iterations);
 }
@@ -1197,6 +1241,8 @@ int sm_destroy(sm_ctx* c) {
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (void* p : c->user_fields) cudaFree(p);
+    if (c->coop_hop) cudaFree(c->coop_hop);
+    if (c->coop_wsum) cudaFree(c->coop_wsum);
     for (auto& g : c->cg_graphs) cudaGraphExecDestroy(g.exec);
     if (c->h) cudaFreeHost(c->h);
     cudaEventDestroy(c->ev_a);

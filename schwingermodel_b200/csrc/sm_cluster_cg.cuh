@@ -1,13 +1,20 @@
 // sm_cluster_cg.cuh -- the whole conjugate gradient of a SMALL lattice in one kernel launch.
 //
-// Lattices up to 16 x 256 = 4096 sites (64 x 64, BASELINE configs[0]) are latency-bound, not
-// bandwidth-bound: a CG iteration touches 128 KiB per field, so what limits a kernel-per-pass
-// design is the launch and dependency latency of ~4000 tiny kernels per HMC trajectory.  Here ONE
-// thread-block cluster (<= 16 CTAs, one lattice site per thread) keeps x, r, d and the four links
-// a site needs in REGISTERS for the entire solve; neighbours exchange pre-projected half-spinors
-// through distributed shared memory (each site publishes 4 complex numbers, readers fetch them
-// from the owning CTA with cluster.map_shared_rank), and the two global sums of an iteration are
-// reduced through DSMEM as well.  An iteration costs 4 cluster barriers and no HBM traffic at all.
+// Small lattices are latency-bound, not bandwidth-bound: a CG iteration on 64 x 64 touches 128 KiB
+// per field, so what limits a kernel-per-pass design is the launch and dependency latency of
+// ~4000 tiny kernels per HMC trajectory.  Here every lattice site is owned by one thread for the
+// entire solve: r, d and the links the site needs stay in REGISTERS, neighbours exchange
+// pre-projected half-spinors (each site publishes 4 complex numbers per stencil, the same rank-1
+// trick as the halo exchange), and the two global sums of an iteration are reduced in-kernel.
+// One iteration = 2 exchanges + 2 sums = 4 barriers; nothing is re-read from HBM.
+//
+// Two transports for the exchange/barrier, same body:
+//   ClusterComm : one thread-block cluster (<= 16 CTAs x 256 threads = 4096 sites, e.g. 64 x 64,
+//                 BASELINE configs[0]); half-spinors and partial sums travel through DISTRIBUTED
+//                 SHARED MEMORY (cluster.map_shared_rank), barrier = cluster.sync (~0.3 us).
+//   GridComm    : a cooperative grid (one 512-thread CTA per SM, up to ~75 k sites, e.g. 256 x 256,
+//                 BASELINE configs[1]); half-spinors travel through L2-resident global buffers,
+//                 barrier = grid.sync.
 // The algorithm is exactly src/conjugate_gradient.cpp:4-67 (x0 = phi, complex alpha, recursive
 // residual, ||r|| < tol ||phi||).
 #pragma once
@@ -21,8 +28,9 @@ namespace cgx = cooperative_groups;
 
 constexpr int kClusterMaxCtas = 16;
 constexpr int kClusterThreads = 256;
+constexpr int kCoopThreads = 512;
 
-struct ClusterCgArgs {
+struct ResidentCgArgs {
     const cplx* U;
     const cplx* phi;
     cplx* x;
@@ -32,48 +40,116 @@ struct ClusterCgArgs {
     double tol;
     int max_iter;
     CgState* st;
+    // GridComm only
+    cplx* hop;          // [2 buffers][4 kinds][V]
+    double* wsum;       // [2 slots][2 values][blocks * warps]
 };
 
+// ---- transport 1: thread-block cluster, distributed shared memory -------------------------------
 struct ClusterShared {
-    double2 hop[2][4][kClusterThreads];                    // [buffer][kind][site slot]
-    double wsum[2][2][kClusterThreads / 32];               // [slot][value][warp]
+    double2 hop[2][4][kClusterThreads];        // [buffer][kind][site slot]
+    double wsum[2][2][kClusterThreads / 32];   // [slot][value][warp]
 };
 
-// sum over the whole cluster of up to two values per thread; one cluster barrier
-template <int NV>
-__device__ __forceinline__ void cluster_sum(cgx::cluster_group& cluster, ClusterShared* sh, int slot, double (&v)[NV]) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int W = kClusterThreads / 32;
-#pragma unroll
-    for (int j = 0; j < NV; j++) {
-        v[j] = warp_sum(v[j]);
-        if (lane == 0) sh->wsum[slot][j][warp] = v[j];
-    }
-    cluster.sync();
-    const int nparts = (int)cluster.num_blocks() * W;     // <= 128 warp partials
-#pragma unroll
-    for (int j = 0; j < NV; j++) {
-        double acc = 0.0;
-        for (int p = lane; p < nparts; p += 32) {
-            const double* remote = cluster.map_shared_rank(&sh->wsum[slot][j][0], p / W);
-            acc += remote[p % W];
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        v[j] = acc;                                       // identical in every thread of the cluster
-    }
-}
+struct ClusterComm {
+    static constexpr int kThreads = kClusterThreads;
+    cgx::cluster_group cluster;
+    ClusterShared* sh;
+    const double2 *q_tp, *q_tm, *q_xp, *q_xm;   // remote views of hop[0][kind][neighbour slot]
 
-__global__ void __launch_bounds__(kClusterThreads, 1) k_cg_cluster(const ClusterCgArgs a) {
-    cgx::cluster_group cluster = cgx::this_cluster();
-    __shared__ ClusterShared sh;
-    const int tid = threadIdx.x;
-    const int n = (int)cluster.block_rank() * kClusterThreads + tid;   // this thread's site
+    __device__ ClusterComm(ClusterShared* s) : cluster(cgx::this_cluster()), sh(s) {}
+    __device__ int site() const { return (int)cluster.block_rank() * kThreads + (int)threadIdx.x; }
+    __device__ void bind(int m_tp, int m_tm, int m_xp, int m_xm) {
+        q_tp = cluster.map_shared_rank(&sh->hop[0][0][0], m_tp / kThreads) + (m_tp % kThreads);
+        q_tm = cluster.map_shared_rank(&sh->hop[0][1][0], m_tm / kThreads) + (m_tm % kThreads);
+        q_xp = cluster.map_shared_rank(&sh->hop[0][2][0], m_xp / kThreads) + (m_xp % kThreads);
+        q_xm = cluster.map_shared_rank(&sh->hop[0][3][0], m_xm / kThreads) + (m_xm % kThreads);
+    }
+    __device__ void put(int buf, int kind, cplx v) { sh->hop[buf][kind][threadIdx.x] = v; }
+    __device__ cplx get_tp(int buf) const { return q_tp[buf * 4 * kThreads]; }
+    __device__ cplx get_tm(int buf) const { return q_tm[buf * 4 * kThreads]; }
+    __device__ cplx get_xp(int buf) const { return q_xp[buf * 4 * kThreads]; }
+    __device__ cplx get_xm(int buf) const { return q_xm[buf * 4 * kThreads]; }
+    __device__ void barrier() { cluster.sync(); }
+
+    // sum over all threads of the cluster, identical result everywhere; one barrier
+    template <int NV>
+    __device__ void sum(int slot, double (&v)[NV]) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        constexpr int W = kThreads / 32;
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            v[j] = warp_sum(v[j]);
+            if (lane == 0) sh->wsum[slot][j][warp] = v[j];
+        }
+        cluster.sync();
+        const int nparts = (int)cluster.num_blocks() * W;   // <= 128 warp partials
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            double acc = 0.0;
+            for (int p = lane; p < nparts; p += 32) {
+                const double* remote = cluster.map_shared_rank(&sh->wsum[slot][j][0], p / W);
+                acc += remote[p % W];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            v[j] = acc;
+        }
+    }
+};
+
+// ---- transport 2: cooperative grid, L2-resident global buffers ----------------------------------
+struct GridComm {
+    static constexpr int kThreads = kCoopThreads;
+    cgx::grid_group grid;
+    cplx* hop;
+    double* wsum;
+    int V, n, nparts;
+    int m_tp, m_tm, m_xp, m_xm;
+
+    __device__ GridComm(const ResidentCgArgs& a)
+        : grid(cgx::this_grid()), hop(a.hop), wsum(a.wsum), V(a.V),
+          n((int)blockIdx.x * kThreads + (int)threadIdx.x), nparts((int)gridDim.x * (kThreads / 32)) {}
+    __device__ int site() const { return n; }
+    __device__ void bind(int tp, int tm, int xp, int xm) { m_tp = tp; m_tm = tm; m_xp = xp; m_xm = xm; }
+    __device__ void put(int buf, int kind, cplx v) {
+        if (n < V) __stcg(&hop[(size_t)(buf * 4 + kind) * V + n], v);
+    }
+    __device__ cplx get_tp(int buf) const { return __ldcg(&hop[(size_t)(buf * 4 + 0) * V + m_tp]); }
+    __device__ cplx get_tm(int buf) const { return __ldcg(&hop[(size_t)(buf * 4 + 1) * V + m_tm]); }
+    __device__ cplx get_xp(int buf) const { return __ldcg(&hop[(size_t)(buf * 4 + 2) * V + m_xp]); }
+    __device__ cplx get_xm(int buf) const { return __ldcg(&hop[(size_t)(buf * 4 + 3) * V + m_xm]); }
+    __device__ void barrier() { grid.sync(); }
+
+    template <int NV>
+    __device__ void sum(int slot, double (&v)[NV]) {
+        const int lane = threadIdx.x & 31;
+        const int gw = (int)blockIdx.x * (kThreads / 32) + ((int)threadIdx.x >> 5);
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            v[j] = warp_sum(v[j]);
+            if (lane == 0) __stcg(&wsum[(size_t)(slot * 2 + j) * nparts + gw], v[j]);
+        }
+        grid.sync();
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            double acc = 0.0;
+            for (int p = lane; p < nparts; p += 32) acc += __ldcg(&wsum[(size_t)(slot * 2 + j) * nparts + p]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            v[j] = acc;   // every warp adds the same numbers in the same order
+        }
+    }
+};
+
+// ---- the solve ------------------------------------------------------------------------------------
+template <class Comm>
+__device__ __forceinline__ void resident_cg(const ResidentCgArgs& a, Comm& comm) {
+    const int n = comm.site();
     const bool active = n < a.V;
     const int wt = a.wt, wx = a.wx, V = a.V;
 
-    // neighbours: owning CTA and slot there
-    int m_tp = n, m_tm = n, m_xp = n, m_xm = n;
+    int m_tp = 0, m_tm = 0, m_xp = 0, m_xm = 0;
     double sR = 1.0, sL = 1.0;
     if (active) {
         const int x = n / wt, t = n - x * wt;
@@ -84,12 +160,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_cg_cluster(const Cluster
         sR = (t == wt - 1) ? a.sR_edge : 1.0;
         sL = (t == 0) ? a.sL_edge : 1.0;
     }
-    // remote views of hop[0][kind][slot]; buffer 1 sits 4*kClusterThreads entries further
-    const double2* q_tp = cluster.map_shared_rank(&sh.hop[0][0][0], m_tp / kClusterThreads) + (m_tp % kClusterThreads);
-    const double2* q_tm = cluster.map_shared_rank(&sh.hop[0][1][0], m_tm / kClusterThreads) + (m_tm % kClusterThreads);
-    const double2* q_xp = cluster.map_shared_rank(&sh.hop[0][2][0], m_xp / kClusterThreads) + (m_xp % kClusterThreads);
-    const double2* q_xm = cluster.map_shared_rank(&sh.hop[0][3][0], m_xm / kClusterThreads) + (m_xm % kClusterThreads);
-    constexpr int kBuf = 4 * kClusterThreads;
+    comm.bind(m_tp, m_tm, m_xp, m_xm);
 
     const cplx zero = make_double2(0.0, 0.0);
     cplx u0 = zero, u1 = zero, f0 = zero, f1 = zero;
@@ -100,46 +171,52 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_cg_cluster(const Cluster
         f1 = a.phi[V + n];
     }
 
-    // one stencil application: publish the four half-spinors of (p0,p1), barrier, gather
+    // one stencil application = publish the four half-spinors of (p0,p1), barrier, gather
     auto publish = [&](auto hop_tag, int buf, cplx p0, cplx p1) {
         using H = decltype(hop_tag);
-        sh.hop[buf][0][tid] = H::from_tp(p0, p1);
-        sh.hop[buf][1][tid] = cmulc(u0, H::from_tm(p0, p1));
-        sh.hop[buf][2][tid] = H::from_xp(p0, p1);
-        sh.hop[buf][3][tid] = cmulc(u1, H::from_xm(p0, p1));
+        comm.put(buf, 0, H::from_tp(p0, p1));
+        comm.put(buf, 1, cmulc(u0, H::from_tm(p0, p1)));
+        comm.put(buf, 2, H::from_xp(p0, p1));
+        comm.put(buf, 3, cmulc(u1, H::from_xm(p0, p1)));
     };
     auto gather = [&](auto hop_tag, int buf, cplx p0, cplx p1, cplx& o0, cplx& o1) {
         using H = decltype(hop_tag);
         cplx a0, a1;
-        H::add_tp(cscale(sR, cmul(u0, q_tp[buf * kBuf])), a0, a1);
-        H::add_xp(cmul(u1, q_xp[buf * kBuf]), a0, a1);
-        H::add_tm(cscale(sL, q_tm[buf * kBuf]), a0, a1);
-        H::add_xm(q_xm[buf * kBuf], a0, a1);
+        H::add_tp(cscale(sR, cmul(u0, comm.get_tp(buf))), a0, a1);
+        H::add_xp(cmul(u1, comm.get_xp(buf)), a0, a1);
+        H::add_tm(cscale(sL, comm.get_tm(buf)), a0, a1);
+        H::add_xm(comm.get_xm(buf), a0, a1);
         o0 = make_double2(a.mass * p0.x - 0.5 * a0.x, a.mass * p0.y - 0.5 * a0.y);
         o1 = make_double2(a.mass * p1.x - 0.5 * a1.x, a.mass * p1.y - 0.5 * a1.y);
     };
-    // out = D D^dagger p   (two exchanges, two cluster barriers)
+    // out = D D^dagger p : two exchanges, two barriers.  Buffer 0 carries psi, buffer 1 carries t;
+    // a buffer is rewritten only after a later barrier than the one its readers waited on.
     auto dd = [&](cplx p0, cplx p1, cplx& o0, cplx& o1) {
         cplx t0, t1;
         publish(Hop<true>{}, 0, p0, p1);
-        cluster.sync();
+        comm.barrier();
         gather(Hop<true>{}, 0, p0, p1, t0, t1);
         publish(Hop<false>{}, 1, t0, t1);
-        cluster.sync();
+        comm.barrier();
         gather(Hop<false>{}, 1, t0, t1, o0, o1);
     };
 
-    // x = phi ; r = phi - D D^dagger phi ; d = r   (conjugate_gradient.cpp:16-24)
-    cplx x0 = f0, x1 = f1, r0, r1, d0, d1, A0, A1;
-    dd(x0, x1, A0, A1);
+    // x = phi ; r = phi - D D^dagger phi ; d = r   (conjugate_gradient.cpp:16-24).
+    // x lives in global memory: it is only ever updated in place, never exchanged.
+    cplx r0, r1, d0, d1, A0, A1;
+    dd(f0, f1, A0, A1);
     r0 = csub(f0, A0);
     r1 = csub(f1, A1);
     if (!active) r0 = r1 = zero;
     d0 = r0;
     d1 = r1;
+    if (active) {
+        a.x[n] = f0;
+        a.x[V + n] = f1;
+    }
     double s2[2] = {f0.x * f0.x + f0.y * f0.y + f1.x * f1.x + f1.y * f1.y,
                     r0.x * r0.x + r0.y * r0.y + r1.x * r1.x + r1.y * r1.y};
-    cluster_sum<2>(cluster, &sh, 1, s2);
+    comm.template sum<2>(1, s2);
     const double phi_norm = sqrt(s2[0]);
     double rr = s2[1];
 
@@ -147,32 +224,35 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_cg_cluster(const Cluster
     while (k < a.max_iter) {
         dd(d0, d1, A0, A1);
         if (!active) A0 = A1 = zero;
-        // alpha = r_norm2 / dot(d, Ad)
+        // alpha = r_norm2 / dot(d, Ad)   (:33)
         const cplx q0 = cmul_conj(d0, A0), q1 = cmul_conj(d1, A1);
         double dAd[2] = {q0.x + q1.x, q0.y + q1.y};
-        cluster_sum<2>(cluster, &sh, 0, dAd);
+        cplx x0 = zero, x1 = zero;                      // fetched here so the latency hides behind the sum's barrier
+        if (active) {
+            x0 = a.x[n];
+            x1 = a.x[V + n];
+        }
+        comm.template sum<2>(0, dAd);
         const cplx alpha = cdiv(make_double2(rr, 0.0), make_double2(dAd[0], dAd[1]));
-        x0 = cadd(x0, cmul(alpha, d0));
-        x1 = cadd(x1, cmul(alpha, d1));
-        r0 = csub(r0, cmul(alpha, A0));
+        if (active) {                                   // x += alpha d   (:34-36)
+            a.x[n] = cadd(x0, cmul(alpha, d0));
+            a.x[V + n] = cadd(x1, cmul(alpha, d1));
+        }
+        r0 = csub(r0, cmul(alpha, A0));                 // r -= alpha Ad  (:37-41)
         r1 = csub(r1, cmul(alpha, A1));
         double e2[1] = {r0.x * r0.x + r0.y * r0.y + r1.x * r1.x + r1.y * r1.y};
-        cluster_sum<1>(cluster, &sh, 1, e2);
-        if (sqrt(e2[0]) < a.tol * phi_norm) {
+        comm.template sum<1>(1, e2);
+        if (sqrt(e2[0]) < a.tol * phi_norm) {           // :45
             converged = 1;
             break;
         }
-        const double beta = e2[0] / rr;
+        const double beta = e2[0] / rr;                 // :51-59
         d0 = make_double2(d0.x * beta + r0.x, d0.y * beta + r0.y);
         d1 = make_double2(d1.x * beta + r1.x, d1.y * beta + r1.y);
         rr = e2[0];
         k++;
     }
 
-    if (active) {
-        a.x[n] = x0;
-        a.x[V + n] = x1;
-    }
     if (n == 0) {
         a.st->phi_norm2 = s2[0];
         a.st->rr[0] = rr;
@@ -180,7 +260,18 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_cg_cluster(const Cluster
         a.st->converged = converged;
         a.st->done = 1;
     }
-    cluster.sync();   // nobody leaves while a neighbour may still read its shared memory
+    comm.barrier();   // nobody leaves while a neighbour may still read what it published
+}
+
+__global__ void __launch_bounds__(kClusterThreads, 1) k_cg_cluster(const ResidentCgArgs a) {
+    __shared__ ClusterShared sh;
+    ClusterComm comm(&sh);
+    resident_cg(a, comm);
+}
+
+__global__ void __launch_bounds__(kCoopThreads, 1) k_cg_coop(const ResidentCgArgs a) {
+    GridComm comm(a);
+    resident_cg(a, comm);
 }
 
 }  // namespace sm

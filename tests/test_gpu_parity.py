@@ -376,7 +376,7 @@ def test_one_pass_and_two_pass_DDdag_agree(sb):
 def test_cg_execution_strategies_agree(sb):
     """Cluster-resident CG (<= 4096 sites), CUDA-graph batches and plain launches run the same algorithm."""
     from oracle.port import Port, gaussian_fields
-    for nx, nt, m0 in [(64, 64, 0.0), (16, 24, -0.05), (48, 80, 0.02), (5, 7, 0.3)]:
+    for nx, nt, m0 in [(64, 64, 0.0), (16, 24, -0.05), (96, 100, 0.02), (5, 7, 0.3)]:   # cluster, cluster, grid, cluster
         P = Port(nx, nt)
         U = P.hot_start(5)
         phi, _ = gaussian_fields(nx, nt, 6)
