@@ -169,6 +169,7 @@ struct sm_ctx {
     int coop_sites = -1;
     cplx* coop_hop = nullptr;
     double* coop_wsum = nullptr;
+    unsigned int* coop_bar = nullptr;
 
     bool dist() const { return nranks > 1; }
     double sR_edge() const { return (ct == rt - 1) ? -1.0 : 1.0; }
@@ -794,9 +795,12 @@ static int dev_cg_coop(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, doubl
     if (!c->coop_hop) {
         TRY(dev_alloc(&c->coop_hop, (size_t)8 * c->V));
         TRY(dev_alloc(&c->coop_wsum, (size_t)4 * blocks * (kCoopThreads / 32)));
+        TRY(dev_alloc(&c->coop_bar, (size_t)32));
     }
+    CU(cudaMemsetAsync(c->coop_bar, 0, sizeof(unsigned int) * 32, c->stream));
     a.hop = c->coop_hop;
     a.wsum = c->coop_wsum;
+    a.bar = c->coop_bar;
     void* params[] = {&a};
     CU(cudaLaunchCooperativeKernel((const void*)k_cg_coop, dim3(blocks, 1, 1), dim3(kCoopThreads, 1, 1), params, 0,
                                    c->stream));
@@ -1243,6 +1247,7 @@ int sm_destroy(sm_ctx* c) {
     for (void* p : c->user_fields) cudaFree(p);
     if (c->coop_hop) cudaFree(c->coop_hop);
     if (c->coop_wsum) cudaFree(c->coop_wsum);
+    if (c->coop_bar) cudaFree(c->coop_bar);
     for (auto& g : c->cg_graphs) cudaGraphExecDestroy(g.exec);
     if (c->h) cudaFreeHost(c->h);
     cudaEventDestroy(c->ev_a);

@@ -14,7 +14,7 @@
 //                 SHARED MEMORY (cluster.map_shared_rank), barrier = cluster.sync (~0.3 us).
 //   GridComm    : a cooperative grid (one 512-thread CTA per SM, up to ~75 k sites, e.g. 256 x 256,
 //                 BASELINE configs[1]); half-spinors travel through L2-resident global buffers,
-//                 barrier = grid.sync.
+//                 barrier = one release/acquire counter in L2 (cooperative launch for co-residency).
 // The algorithm is exactly src/conjugate_gradient.cpp:4-67 (x0 = phi, complex alpha, recursive
 // residual, ||r|| < tol ||phi||).
 #pragma once
@@ -43,6 +43,7 @@ struct ResidentCgArgs {
     // GridComm only
     cplx* hop;          // [2 buffers][4 kinds][V]
     double* wsum;       // [2 slots][2 values][blocks * warps]
+    unsigned int* bar;  // monotonic arrival counter of the grid barrier (zeroed before the launch)
 };
 
 // ---- transport 1: thread-block cluster, distributed shared memory -------------------------------
@@ -53,6 +54,7 @@ struct ClusterShared {
 
 struct ClusterComm {
     static constexpr int kThreads = kClusterThreads;
+    static constexpr bool kXInRegisters = true;      // 1 CTA per SM, registers to spare
     cgx::cluster_group cluster;
     ClusterShared* sh;
     const double2 *q_tp, *q_tm, *q_xp, *q_xm;   // remote views of hop[0][kind][neighbour slot]
@@ -101,14 +103,16 @@ struct ClusterComm {
 // ---- transport 2: cooperative grid, L2-resident global buffers ----------------------------------
 struct GridComm {
     static constexpr int kThreads = kCoopThreads;
-    cgx::grid_group grid;
+    static constexpr bool kXInRegisters = false;     // 128-register budget: x is updated in place in L2
     cplx* hop;
     double* wsum;
+    unsigned int* bar;
+    unsigned int target;                             // arrivals expected at the next barrier
     int V, n, nparts;
     int m_tp, m_tm, m_xp, m_xm;
 
     __device__ GridComm(const ResidentCgArgs& a)
-        : grid(cgx::this_grid()), hop(a.hop), wsum(a.wsum), V(a.V),
+        : hop(a.hop), wsum(a.wsum), bar(a.bar), target(0), V(a.V),
           n((int)blockIdx.x * kThreads + (int)threadIdx.x), nparts((int)gridDim.x * (kThreads / 32)) {}
     __device__ int site() const { return n; }
     __device__ void bind(int tp, int tm, int xp, int xm) { m_tp = tp; m_tm = tm; m_xp = xp; m_xm = xm; }
@@ -119,7 +123,23 @@ struct GridComm {
     __device__ cplx get_tm(int buf) const { return __ldcg(&hop[(size_t)(buf * 4 + 1) * V + m_tm]); }
     __device__ cplx get_xp(int buf) const { return __ldcg(&hop[(size_t)(buf * 4 + 2) * V + m_xp]); }
     __device__ cplx get_xm(int buf) const { return __ldcg(&hop[(size_t)(buf * 4 + 3) * V + m_xm]); }
-    __device__ void barrier() { grid.sync(); }
+    // Grid barrier on one monotonic counter: thread 0 of every CTA arrives with a release and spins
+    // with acquire loads until all CTAs of this round have arrived (the cooperative launch
+    // guarantees they are co-resident).  About 3x cheaper than cooperative_groups' grid.sync here.
+    __device__ void barrier() {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            target += gridDim.x;
+            unsigned int seen;
+            __threadfence();   // the CTA's stores (ordered before this point by the block barrier) go out first
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+            } while (seen < target);
+            __threadfence();
+        }
+        __syncthreads();
+    }
 
     template <int NV>
     __device__ void sum(int slot, double (&v)[NV]) {
@@ -130,7 +150,7 @@ struct GridComm {
             v[j] = warp_sum(v[j]);
             if (lane == 0) __stcg(&wsum[(size_t)(slot * 2 + j) * nparts + gw], v[j]);
         }
-        grid.sync();
+        barrier();
 #pragma unroll
         for (int j = 0; j < NV; j++) {
             double acc = 0.0;
@@ -210,7 +230,8 @@ __device__ __forceinline__ void resident_cg(const ResidentCgArgs& a, Comm& comm)
     if (!active) r0 = r1 = zero;
     d0 = r0;
     d1 = r1;
-    if (active) {
+    cplx xr0 = f0, xr1 = f1;                            // x when it is kept in registers
+    if (!Comm::kXInRegisters && active) {
         a.x[n] = f0;
         a.x[V + n] = f1;
     }
@@ -228,13 +249,16 @@ __device__ __forceinline__ void resident_cg(const ResidentCgArgs& a, Comm& comm)
         const cplx q0 = cmul_conj(d0, A0), q1 = cmul_conj(d1, A1);
         double dAd[2] = {q0.x + q1.x, q0.y + q1.y};
         cplx x0 = zero, x1 = zero;                      // fetched here so the latency hides behind the sum's barrier
-        if (active) {
+        if (!Comm::kXInRegisters && active) {
             x0 = a.x[n];
             x1 = a.x[V + n];
         }
         comm.template sum<2>(0, dAd);
         const cplx alpha = cdiv(make_double2(rr, 0.0), make_double2(dAd[0], dAd[1]));
-        if (active) {                                   // x += alpha d   (:34-36)
+        if (Comm::kXInRegisters) {                      // x += alpha d   (:34-36)
+            xr0 = cadd(xr0, cmul(alpha, d0));
+            xr1 = cadd(xr1, cmul(alpha, d1));
+        } else if (active) {
             a.x[n] = cadd(x0, cmul(alpha, d0));
             a.x[V + n] = cadd(x1, cmul(alpha, d1));
         }
@@ -253,6 +277,10 @@ __device__ __forceinline__ void resident_cg(const ResidentCgArgs& a, Comm& comm)
         k++;
     }
 
+    if (Comm::kXInRegisters && active) {
+        a.x[n] = xr0;
+        a.x[V + n] = xr1;
+    }
     if (n == 0) {
         a.st->phi_norm2 = s2[0];
         a.st->rr[0] = rr;
