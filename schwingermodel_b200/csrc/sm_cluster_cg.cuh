@@ -49,7 +49,8 @@ struct ResidentCgArgs {
 // ---- transport 1: thread-block cluster, distributed shared memory -------------------------------
 struct ClusterShared {
     double2 hop[2][4][kClusterThreads];        // [buffer][kind][site slot]
-    double wsum[2][2][kClusterThreads / 32];   // [slot][value][warp]
+    double wpart[2][kClusterThreads / 32];     // [value][warp]   scratch of the CTA-level step
+    double wsum[2][2];                         // [slot][value]   this CTA's partial, read by the whole cluster
 };
 
 struct ClusterComm {
@@ -74,7 +75,8 @@ struct ClusterComm {
     __device__ cplx get_xm(int buf) const { return q_xm[buf * 4 * kThreads]; }
     __device__ void barrier() { cluster.sync(); }
 
-    // sum over all threads of the cluster, identical result everywhere; one barrier
+    // sum over all threads of the cluster, identical result everywhere: warp shuffle -> CTA partial in
+    // shared memory -> cluster barrier -> every warp adds the <= 16 CTA partials (one DSMEM load per lane)
     template <int NV>
     __device__ void sum(int slot, double (&v)[NV]) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -82,17 +84,23 @@ struct ClusterComm {
 #pragma unroll
         for (int j = 0; j < NV; j++) {
             v[j] = warp_sum(v[j]);
-            if (lane == 0) sh->wsum[slot][j][warp] = v[j];
+            if (lane == 0) sh->wpart[j][warp] = v[j];
+        }
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll
+            for (int j = 0; j < NV; j++) {
+                double x = (lane < W) ? sh->wpart[j][lane] : 0.0;
+                x = warp_sum(x);
+                if (lane == 0) sh->wsum[slot][j] = x;
+            }
         }
         cluster.sync();
-        const int nparts = (int)cluster.num_blocks() * W;   // <= 128 warp partials
+        const int nb = (int)cluster.num_blocks();
 #pragma unroll
         for (int j = 0; j < NV; j++) {
             double acc = 0.0;
-            for (int p = lane; p < nparts; p += 32) {
-                const double* remote = cluster.map_shared_rank(&sh->wsum[slot][j][0], p / W);
-                acc += remote[p % W];
-            }
+            if (lane < nb) acc = *cluster.map_shared_rank(&sh->wsum[slot][j], lane);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             v[j] = acc;
@@ -108,12 +116,12 @@ struct GridComm {
     double* wsum;
     unsigned int* bar;
     unsigned int target;                             // arrivals expected at the next barrier
-    int V, n, nparts;
+    int V, n;
     int m_tp, m_tm, m_xp, m_xm;
 
     __device__ GridComm(const ResidentCgArgs& a)
         : hop(a.hop), wsum(a.wsum), bar(a.bar), target(0), V(a.V),
-          n((int)blockIdx.x * kThreads + (int)threadIdx.x), nparts((int)gridDim.x * (kThreads / 32)) {}
+          n((int)blockIdx.x * kThreads + (int)threadIdx.x) {}
     __device__ int site() const { return n; }
     __device__ void bind(int tp, int tm, int xp, int xm) { m_tp = tp; m_tm = tm; m_xp = xp; m_xm = xm; }
     __device__ void put(int buf, int kind, cplx v) {
@@ -141,23 +149,39 @@ struct GridComm {
         __syncthreads();
     }
 
+    // warp shuffle -> CTA partial (shared) -> L2 -> grid barrier -> every warp adds the <= 160 CTA
+    // partials with independent loads, in a fixed order
     template <int NV>
     __device__ void sum(int slot, double (&v)[NV]) {
-        const int lane = threadIdx.x & 31;
-        const int gw = (int)blockIdx.x * (kThreads / 32) + ((int)threadIdx.x >> 5);
+        __shared__ double wpart[2][kThreads / 32];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        constexpr int W = kThreads / 32;
+        const int nb = (int)gridDim.x;
 #pragma unroll
         for (int j = 0; j < NV; j++) {
             v[j] = warp_sum(v[j]);
-            if (lane == 0) __stcg(&wsum[(size_t)(slot * 2 + j) * nparts + gw], v[j]);
+            if (lane == 0) wpart[j][warp] = v[j];
+        }
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll
+            for (int j = 0; j < NV; j++) {
+                double x = (lane < W) ? wpart[j][lane] : 0.0;
+                x = warp_sum(x);
+                if (lane == 0) __stcg(&wsum[(size_t)(slot * 2 + j) * nb + blockIdx.x], x);
+            }
         }
         barrier();
 #pragma unroll
         for (int j = 0; j < NV; j++) {
-            double acc = 0.0;
-            for (int p = lane; p < nparts; p += 32) acc += __ldcg(&wsum[(size_t)(slot * 2 + j) * nparts + p]);
+            const double* part = wsum + (size_t)(slot * 2 + j) * nb;
+            double p[5];
+#pragma unroll
+            for (int i = 0; i < 5; i++) p[i] = (lane + 32 * i < nb) ? __ldcg(part + lane + 32 * i) : 0.0;
+            double acc = ((p[0] + p[1]) + (p[2] + p[3])) + p[4];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            v[j] = acc;   // every warp adds the same numbers in the same order
+            v[j] = acc;
         }
     }
 };
