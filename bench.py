@@ -258,6 +258,12 @@ def run_b200(args):
     L = args.lattice
     m0, beta = 0.0, 2.0
     lat = sb.Lattice(L, L, device=local_rank, ranks_x=N, ranks_t=1, rank=rank, nccl_id=nccl_id)
+    halo = "none"
+    if N > 1:
+        halo = "nccl send/recv"
+        if os.environ.get("SM_P2P", "1") != "0":
+            lat.p2p_connect_all(dist)       # halo rows stored straight into the neighbour's HBM over NVLink
+            halo = "peer-memory stores (CUDA IPC) + stream-ordered flag waits"
     V = lat.V
     U_h = synthetic_links(V, 1000 + rank)
     phi_h = synthetic_spinor(V, 2000 + rank)
@@ -328,15 +334,40 @@ def run_b200(args):
         "config": {"workload": f"DD^dagger on {L}x{L}, beta=2, m0=0, hot-start links, Gaussian source "
                                f"(BASELINE configs[3]); ranks_x={N}, ranks_t=1",
                    "l2": "inputs larger than L2 (each field %.0f MiB per GPU)" % (V * 32 / 2 ** 20),
-                   "step": "one D D^dagger application over the whole lattice"},
+                   "step": "one D D^dagger application over the whole lattice", "halo_exchange": halo},
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "hbm_gbs_effective": BYTES_PER_DD_SITE * value / 1e9 / N,
     }
 
-    # ---- the other two parts of BASELINE.json's metric (rank 0, single GPU) -------------------------
-    if N == 1 and not args.skip_extra:
-        line["extra"] = extra_metrics(sb, args)
-        line["cpu_baseline"] = cpu_baseline(args)
+    # ---- the other two parts of BASELINE.json's metric: CG solves/s and HMC trajectories/s -----------
+    if not args.skip_extra:
+        # on the bench lattice itself, at this GPU count (device-resident, max over ranks)
+        big = {}
+        dx = lat.new_field(True)
+        lat.set_cg(1e-10, 10000)
+        barrier()
+        t0 = time.perf_counter()
+        ok, its = lat.dev_cg(dU, dphi, dx, m0)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        big["cg"] = {"solves_per_s": 1.0 / dt, "iterations": its, "converged": ok, "seconds": dt,
+                     "GBs_per_gpu_320B": 320.0 * V * (its + 1) / dt / 1e9,
+                     "config": f"one (D D^dagger)^-1 solve on {L}x{L}, hot start, m0=0, tol 1e-10, device-resident"}
+        for f in (dx, dout):
+            f.free()
+        h = sb.HMC(lat, U_h, 10, 1.0, 0, 0, 0, beta, m0, seed=11)
+        barrier()
+        t0 = time.perf_counter()
+        r, acc = h.HMC_Update()
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        big["hmc"] = {"traj_per_s": 1.0 / dt, "seconds": dt, "dd_applications": int(r.dd_applications),
+                      "cg_solves": int(r.cg_solves), "all_cg_converged": bool(r.cg_all_converged), "dH": r.dH,
+                      "config": f"one HMC trajectory on {L}x{L}, beta=2, m0=0, MD=10, tau=1, hot start, device-resident"}
+        line["extra"] = {f"lattice_{L}": big}
+        if N == 1:
+            line["extra"].update(extra_metrics(sb, args))
+            line["cpu_baseline"] = cpu_baseline(args)
     if rank == 0:
         print(json.dumps(line))
     lat.close()

@@ -51,6 +51,7 @@ enum {
 };
 
 #define SM_NCCL_ID_BYTES 128
+#define SM_P2P_HANDLE_BYTES 64
 
 /* ---- life cycle ------------------------------------------------------------------------------
  * replaces initializeMPI() + allocate_lattice_arrays() + periodic_boundary()
@@ -60,6 +61,11 @@ SM_API int sm_create(int Nx, int Nt, int device, sm_ctx** out);
  * nccl_id: SM_NCCL_ID_BYTES bytes from sm_nccl_unique_id() on rank 0, broadcast by the caller. */
 SM_API int sm_create_dist(int Nx, int Nt, int ranks_x, int ranks_t, int rank, int device, const void* nccl_id, sm_ctx** out);
 SM_API int sm_nccl_unique_id(void* out_id /* SM_NCCL_ID_BYTES */);
+/* Optional, lattices split along x only: halo rows are stored straight into the neighbour's memory over
+ * NVLink (CUDA IPC) instead of ncclSend/ncclRecv.  Every rank exports a handle, the caller gathers the
+ * ranks' handles in rank order (MPI_Allgather in the reference's world) and every rank connects. */
+SM_API int sm_p2p_handle(sm_ctx* ctx, void* handle_out /* SM_P2P_HANDLE_BYTES */);
+SM_API int sm_p2p_connect(sm_ctx* ctx, const void* all_handles /* nranks * SM_P2P_HANDLE_BYTES, rank order */);
 SM_API int sm_destroy(sm_ctx* ctx);
 SM_API const char* sm_last_error(void);
 /* local tile: dims[0]=width_x, dims[1]=width_t, dims[2]=rank, dims[3]=nranks */

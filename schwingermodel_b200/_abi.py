@@ -16,6 +16,7 @@ HEADER_PATH = os.path.join(ROOT, "include", "schwinger_b200.h")
 
 SM_OK, SM_ERR_ARG, SM_ERR_CUDA, SM_ERR_NCCL, SM_ERR_IO, SM_ERR_STATE = range(6)
 SM_NCCL_ID_BYTES = 128
+SM_P2P_HANDLE_BYTES = 64
 
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int)
@@ -52,6 +53,8 @@ _SIGS = {
     "sm_create": [C.c_int, C.c_int, C.c_int, C.POINTER(ctx_p)],
     "sm_create_dist": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(ctx_p)],
     "sm_nccl_unique_id": [C.c_void_p],
+    "sm_p2p_handle": [ctx_p, C.c_void_p],
+    "sm_p2p_connect": [ctx_p, C.c_void_p],
     "sm_destroy": [ctx_p],
     "sm_local_dims": [ctx_p, ip],
     "sm_set_cg": [ctx_p, C.c_double, C.c_int],

@@ -2,6 +2,7 @@
 // See include/schwinger_b200.h for the contract; DESIGN.md for the layout and kernel list.
 #include "../../include/schwinger_b200.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
@@ -152,6 +153,16 @@ struct sm_ctx {
     cplx *f2_U[2] = {nullptr, nullptr}, *f2_in[2] = {nullptr, nullptr}, *f2_r[2] = {nullptr, nullptr};
     cplx *f2_d[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [ping-pong][lo/hi]
     const cplx* f2_U_valid_for = nullptr;
+    // peer-memory halo push (sm_p2p_connect): one window per rank, [kind: psi, r][parity][side: lo, hi][4 wt]
+    // complex + 4 epoch flags; neighbours store into it over NVLink
+    cplx* win = nullptr;
+    unsigned int* win_flags = nullptr;
+    size_t win_bytes = 0;
+    void* peer_win[2] = {nullptr, nullptr};   // -x, +x neighbour's window (peer pointers)
+    bool p2p = false;
+    unsigned int p2p_epoch[2] = {0, 0};
+    unsigned int* push_ticket = nullptr;
+    CUresult (*wait_value32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
 
     std::vector<void*> user_fields;
 
@@ -418,6 +429,41 @@ static int dev_D(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, double m0,
 }
 
 // D D^dagger via the context's scratch field (the reference's global DTEMP, dirac_operator.cpp:477-480)
+// ---- peer-memory window ------------------------------------------------------------------------
+static size_t win_ghost_elems(const sm_ctx* c) { return 4 * (size_t)c->wt; }
+static cplx* win_ghost(const sm_ctx* c, void* base, int kind, int parity, int side) {
+    return (cplx*)base + (size_t)((kind * 2 + parity) * 2 + side) * win_ghost_elems(c);
+}
+static unsigned int* win_flag(const sm_ctx* c, void* base, int kind, int side) {
+    return (unsigned int*)((char*)base + sizeof(cplx) * 8 * win_ghost_elems(c)) + kind * 2 + side;
+}
+
+// push my boundary rows of `field` into both neighbours' ghosts (epoch parity) and raise their flags
+static int p2p_push(sm_ctx* c, const cplx* field, int kind, cudaStream_t st) {
+    const unsigned int epoch = ++c->p2p_epoch[kind];
+    const int parity = epoch & 1;
+    const int n = 8 * c->wt;
+    const int blocks = std::max(1, std::min(64, (n + kBlock - 1) / kBlock));
+    k_push_rows<<<blocks, kBlock, 0, st>>>(field, c->wx, c->wt, c->V, win_ghost(c, c->peer_win[0], kind, parity, 1),
+                                           win_ghost(c, c->peer_win[1], kind, parity, 0),
+                                           win_flag(c, c->peer_win[0], kind, 1), win_flag(c, c->peer_win[1], kind, 0),
+                                           epoch, c->push_ticket);
+    KCHECK();
+    c->launches++;
+    return SM_OK;
+}
+
+// make `st` wait until both neighbours have delivered the current epoch of `kind`
+static int p2p_wait(sm_ctx* c, int kind, cudaStream_t st) {
+    const unsigned int epoch = c->p2p_epoch[kind];
+    for (int side = 0; side < 2; side++) {
+        CUresult r = c->wait_value32((CUstream)st, (CUdeviceptr)win_flag(c, c->win, kind, side), epoch,
+                                     CU_STREAM_WAIT_VALUE_GEQ);
+        if (r != CUDA_SUCCESS) return fail(SM_ERR_CUDA, "cuStreamWaitValue32 failed (" + std::to_string((int)r) + ")");
+    }
+    return SM_OK;
+}
+
 // two boundary rows of a field (rows 0,1 to the -x neighbour, rows wx-2,wx-1 to the +x neighbour) into
 // the [comp][2][wt] ghost arrays; rows are contiguous in HBM, so nothing is packed
 static int exchange_rows2(sm_ctx* c, const cplx* field, cplx* lo_dst, cplx* hi_dst, cudaStream_t st = nullptr) {
@@ -483,14 +529,22 @@ static int launch_fused(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, dou
         // Only the first and last row chunk read them, so the exchange runs on the comm stream while
         // the interior chunks compute.
         const cplx* moving = (MODE == FUSED_CG) ? r : in;
-        cplx** dst = (MODE == FUSED_CG) ? c->f2_r : c->f2_in;
+        const int kind = (MODE == FUSED_CG) ? 1 : 0;
+        cplx* dst[2] = {(MODE == FUSED_CG) ? c->f2_r[0] : c->f2_in[0], (MODE == FUSED_CG) ? c->f2_r[1] : c->f2_in[1]};
         split_launch = c->overlap && c->fus_split_chunks >= 1;
+        cudaStream_t xs = split_launch ? c->comm_stream : c->stream;
+        if (c->p2p) TRY(p2p_push(c, moving, kind, c->stream));   // stores into the neighbours' windows
         if (split_launch) {
             CU(cudaEventRecord(c->ev_ready, c->stream));
             CU(cudaStreamWaitEvent(c->comm_stream, c->ev_ready, 0));
-            TRY(exchange_rows2(c, moving, dst[0], dst[1], c->comm_stream));
+        }
+        if (c->p2p) {
+            TRY(p2p_wait(c, kind, xs));                           // ... and waits for theirs in mine
+            const int parity = c->p2p_epoch[kind] & 1;
+            dst[0] = win_ghost(c, c->win, kind, parity, 0);
+            dst[1] = win_ghost(c, c->win, kind, parity, 1);
         } else {
-            TRY(exchange_rows2(c, moving, dst[0], dst[1]));
+            TRY(exchange_rows2(c, moving, dst[0], dst[1], xs));
         }
         if (MODE == FUSED_CG) {
             const int cur = k & 1;
@@ -498,11 +552,11 @@ static int launch_fused(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, dou
             a.gin_hi = c->f2_d[cur ^ 1][1];
             a.gd_lo = c->f2_d[cur][0];
             a.gd_hi = c->f2_d[cur][1];
-            a.gr_lo = c->f2_r[0];
-            a.gr_hi = c->f2_r[1];
+            a.gr_lo = dst[0];
+            a.gr_hi = dst[1];
         } else {
-            a.gin_lo = c->f2_in[0];
-            a.gin_hi = c->f2_in[1];
+            a.gin_lo = dst[0];
+            a.gin_hi = dst[1];
         }
     }
     if (split_launch) {
@@ -1234,6 +1288,12 @@ int sm_destroy(sm_ctx* c) {
     if (!c) return SM_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->p2p) {
+        cudaIpcCloseMemHandle(c->peer_win[0]);
+        if (c->peer_win[1] != c->peer_win[0]) cudaIpcCloseMemHandle(c->peer_win[1]);
+    }
+    if (c->win) cudaFree(c->win);
+    if (c->push_ticket) cudaFree(c->push_ticket);
     if (c->comm) g_nccl.CommDestroy(c->comm);
     void* ptrs[] = {c->partials, c->tickets, c->cg,      c->sums,    c->sums_loc, c->tmp,     c->cg_r,   c->cg_d,
                     c->cg_Ad,    c->cg_d2, c->sU,      c->sA,      c->sB,      c->sC,       c->sF,      c->U,      c->Up,
@@ -1323,6 +1383,50 @@ int sm_tables(sm_ctx* c, int ranks_x, int ranks_t, int rank, int* RightPB, int* 
     CU(cudaMemcpyAsync(SignL, dsL, sizeof(double) * 4 * m, cudaMemcpyDeviceToHost, c->stream));
     TRY(sync(c));
     cudaFree(dR); cudaFree(dL); cudaFree(dA); cudaFree(dB); cudaFree(dsR); cudaFree(dsL);
+    return SM_OK;
+}
+
+// ---- peer-memory halo push ------------------------------------------------------------------------
+int sm_p2p_handle(sm_ctx* c, void* handle_out) {
+    TRY(set_device(c));
+    NEED(handle_out);
+    if (!c->dist() || c->rt != 1 || c->wx < 4) return fail(SM_ERR_STATE, "peer-memory halos need a lattice split along x only");
+    if (!c->win) {
+        c->win_bytes = sizeof(cplx) * 8 * win_ghost_elems(c) + 256;
+        CU(cudaMalloc((void**)&c->win, c->win_bytes));
+        CU(cudaMemset(c->win, 0, c->win_bytes));
+        c->win_flags = win_flag(c, c->win, 0, 0);
+        TRY(dev_alloc(&c->push_ticket, (size_t)1));
+        CU(cudaMemset(c->push_ticket, 0, sizeof(unsigned int)));
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == SM_P2P_HANDLE_BYTES, "handle size");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, c->win));
+    memcpy(handle_out, &h, sizeof(h));
+    return SM_OK;
+}
+
+int sm_p2p_connect(sm_ctx* c, const void* all_handles) {
+    TRY(set_device(c));
+    NEED(all_handles);
+    if (!c->win) return fail(SM_ERR_STATE, "sm_p2p_handle first");
+    if (c->p2p) return SM_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qr) != cudaSuccess || fn == nullptr)
+        return fail(SM_ERR_CUDA, "cuStreamWaitValue32 is not available");
+    c->wait_value32 = (CUresult(*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int))fn;
+    const int nb[2] = {c->nb_xm, c->nb_xp};
+    for (int s = 0; s < 2; s++) {
+        if (s == 1 && nb[1] == nb[0]) {
+            c->peer_win[1] = c->peer_win[0];
+            break;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)all_handles + (size_t)nb[s] * SM_P2P_HANDLE_BYTES, sizeof(h));
+        CU(cudaIpcOpenMemHandle(&c->peer_win[s], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    c->p2p = true;
     return SM_OK;
 }
 

@@ -341,4 +341,39 @@ __global__ void __launch_bounds__(kBlock) k_cg_flush_x(CgState* st, cplx* __rest
 
 __global__ void k_cg_clear_pending(CgState* st) { st->pending = 0; }
 
+// ----------------------------------------------------------------------------------------------
+// Halo push over NVLink peer memory (lattice split along x).  Instead of a send/recv pair, the
+// rank that owns the boundary rows stores them straight into the neighbour's ghost arrays
+// (peer pointers from cudaIpcOpenMemHandle) and then raises an epoch flag in the neighbour's
+// memory with a system-scope release; the neighbour's stream waits on its own flag
+// (cuStreamWaitValue32) before the boundary bands of the pass start.  Ghosts are double-buffered
+// on the epoch parity, so a neighbour that runs one pass ahead never overwrites rows still in use.
+//   rows 0,1        -> -x neighbour's "hi" ghost        rows wx-2,wx-1 -> +x neighbour's "lo" ghost
+//   ghost layout [component][2 rows][wt], the same as the NCCL path
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_push_rows(const cplx* __restrict__ field, int wx, int wt, int V,
+                                                      cplx* __restrict__ peer_xm_hi, cplx* __restrict__ peer_xp_lo,
+                                                      unsigned int* flag_xm, unsigned int* flag_xp,
+                                                      unsigned int epoch, unsigned int* ticket) {
+    const int per_side = 4 * wt;
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * per_side; i += stride) {
+        const int side = i / per_side, e = i - side * per_side;
+        const int comp = e / (2 * wt), off = e - comp * 2 * wt;
+        const cplx v = ld_stream(field + (size_t)comp * V + (side == 0 ? 0 : (size_t)(wx - 2) * wt) + off);
+        (side == 0 ? peer_xm_hi : peer_xp_lo)[e] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        if (t == gridDim.x - 1) {           // every block's rows are out: publish the epoch
+            *ticket = 0u;
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag_xm), "r"(epoch) : "memory");
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag_xp), "r"(epoch) : "memory");
+        }
+    }
+}
+
 }  // namespace sm

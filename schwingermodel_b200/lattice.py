@@ -98,6 +98,27 @@ class Lattice:
         check(lib.sm_nccl_unique_id(buf))
         return buf.raw
 
+    # -- peer-memory halos (x-only splits): export, all-gather by the caller, connect ------------------
+    def p2p_handle(self) -> bytes:
+        buf = C.create_string_buffer(_abi.SM_P2P_HANDLE_BYTES)
+        check(self.lib.sm_p2p_handle(self.ctx, buf))
+        return buf.raw
+
+    def p2p_connect(self, handles_in_rank_order):
+        blob = b"".join(handles_in_rank_order)
+        if len(blob) != _abi.SM_P2P_HANDLE_BYTES * self.ranks_x * self.ranks_t:
+            raise ValueError("need one 64-byte handle per rank")
+        buf = C.create_string_buffer(blob, len(blob))
+        check(self.lib.sm_p2p_connect(self.ctx, buf))
+
+    def p2p_connect_all(self, dist_module, device="cuda"):
+        """Gather every rank's window handle with torch.distributed (plumbing only) and connect."""
+        import torch
+        mine = torch.frombuffer(bytearray(self.p2p_handle()), dtype=torch.uint8).to(device)
+        parts = [torch.zeros_like(mine) for _ in range(self.ranks_x * self.ranks_t)]
+        dist_module.all_gather(parts, mine)
+        self.p2p_connect([bytes(p.cpu().numpy().tobytes()) for p in parts])
+
     def close(self):
         if getattr(self, "ctx", None):
             self.lib.sm_destroy(self.ctx)

@@ -43,15 +43,18 @@ def main():
     # every decomposition with the default path choice, and the x-only splits again with the one-pass
     # D D^dagger forced (2-row ghosts), which small lattices would not pick on their own
     cases = [(rx, rt, None) for rx, rt in decomps] + [(rx, rt, "onepass") for rx, rt in decomps if rt == 1 and rx > 1]
+    cases += [(rx, rt, "onepass+p2p") for rx, rt in decomps if rt == 1 and rx > 1 and nx // rx >= 4]
     for rx, rt, path in cases:
         if path:
-            os.environ["SM_DD_PATH"] = path
+            os.environ["SM_DD_PATH"] = "onepass"
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             idt.copy_(torch.frombuffer(bytearray(sb.Lattice.nccl_unique_id()), dtype=torch.uint8))
         dist.broadcast(idt, 0)
         lat = sb.Lattice(nx, nt, device=local, ranks_x=rx, ranks_t=rt, rank=rank, nccl_id=idt.cpu().numpy().tobytes())
         os.environ.pop("SM_DD_PATH", None)
+        if path == "onepass+p2p":
+            lat.p2p_connect_all(dist)     # halo rows by peer-memory stores instead of NCCL send/recv
         T = lambda f: tile_of(f, nx, nt, rx, rt, rank)   # noqa: E731
         tabs, otabs = lat.periodic_boundary(rx, rt, rank), P.tables(rx, rt, rank)
         assert all(np.array_equal(tabs[k], otabs[k]) for k in tabs)
