@@ -75,6 +75,8 @@ SM_API int sm_set_cg(sm_ctx* ctx, double tol, int max_iter);
 /* device time (ms) of the last sm_* call on this context, measured with CUDA events on the
  * context's stream around the kernels only (no copies) */
 SM_API int sm_last_kernel_ms(const sm_ctx* ctx, double* ms);
+/* 1 if D D^dagger runs as the one-pass kernel on this context (single tile or x-only split), 0 if as two stencil passes */
+SM_API int sm_one_pass_dd(const sm_ctx* ctx, int* one_pass);
 /* number of kernels this library launched on the context since creation */
 SM_API int sm_launch_count(const sm_ctx* ctx, long long* n);
 

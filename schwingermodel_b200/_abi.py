@@ -60,6 +60,7 @@ _SIGS = {
     "sm_set_cg": [ctx_p, C.c_double, C.c_int],
     "sm_last_kernel_ms": [ctx_p, dp],
     "sm_launch_count": [ctx_p, C.POINTER(C.c_longlong)],
+    "sm_one_pass_dd": [ctx_p, ip],
     "sm_tables": [ctx_p, C.c_int, C.c_int, C.c_int, ip, ip, dp, dp, ip, ip],
     "sm_D_phi": [ctx_p, dp, dp, dp, dp, dp, dp, C.c_double],
     "sm_D_dagger_phi": [ctx_p, dp, dp, dp, dp, dp, dp, C.c_double],

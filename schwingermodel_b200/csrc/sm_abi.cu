@@ -1347,6 +1347,13 @@ int sm_last_kernel_ms(const sm_ctx* c, double* ms) {
     return SM_OK;
 }
 
+int sm_one_pass_dd(const sm_ctx* c, int* one_pass) {
+    NEED(c);
+    NEED(one_pass);
+    *one_pass = fused_ok(c) ? 1 : 0;
+    return SM_OK;
+}
+
 int sm_launch_count(const sm_ctx* c, long long* n) {
     NEED(c);
     NEED(n);

@@ -145,6 +145,11 @@ class Lattice:
         check(self.lib.sm_launch_count(self.ctx, C.byref(n)))
         return n.value
 
+    def one_pass_dd(self) -> bool:
+        v = C.c_int()
+        check(self.lib.sm_one_pass_dd(self.ctx, C.byref(v)))
+        return bool(v.value)
+
     def new_field(self, complex_field=True, init=None) -> DeviceField:
         f = DeviceField(self, complex_field)
         if init is not None:
