@@ -402,3 +402,41 @@ def test_cg_execution_strategies_agree(sb):
         xref = P.cg(U, phi, m0, 1e-10, 11)[0]
         for name, xm in got.items():
             assert relerr(xm, xref) <= 1e-10, name
+
+
+def test_config2_trajectory_256_vs_oracle(sb):
+    """A full trajectory at BASELINE config 2's size (grid-resident CG path): dH against the oracle."""
+    from oracle.port import Port, gaussian_fields
+    n = 256
+    P, lat = Port(n, n), sb.Lattice(n, n)
+    U = P.hot_start(12345)
+    chi, pi = gaussian_fields(n, n, 777)
+    md, tau, beta, m0 = 4, 0.2, 2.0, 0.0
+    t = P.trajectory(U, pi, chi, md, tau, beta, m0)
+    lat.hmc_configure(beta, m0, md, tau)
+    lat.hmc_set_gauge(U)
+    lat.hmc_inject(pi, chi)
+    r = lat.hmc_trajectory()
+    assert r.cg_all_converged == 1 and t["cg_ok"] == 1
+    assert abs(r.dd_applications - t["dd_apps"]) <= r.cg_solves
+    assert abs(r.dH - t["dH"]) <= TOL_DH, (r.dH, t["dH"])
+    assert np.abs(lat.hmc_get_gauge(True) - t["U"]).max() <= 1e-9
+    lat.close()
+
+
+def test_config5_near_critical_cg_vs_oracle(sb):
+    """BASELINE config 5 parameters (m0 = -0.18, ill-conditioned, long CG) at 128x128: same convergence flag,
+    iteration count within a few per cent, true residual to the stated tolerance."""
+    from oracle.port import Port, gaussian_fields
+    n, m0 = 128, -0.18
+    P, lat = Port(n, n), sb.Lattice(n, n)
+    U = P.hot_start(2024)
+    phi, _ = gaussian_fields(n, n, 31)
+    xo, oko, apps, _ = P.cg(U, phi, m0)
+    x, ok, its = lat.conjugate_gradient(U, phi, m0)
+    assert ok == oko == 1
+    assert abs(its + 2 - apps) <= max(2, apps // 50), (its, apps)
+    res = np.linalg.norm(phi - lat.D_D_dagger_phi(U, x, m0)) / np.linalg.norm(phi)
+    assert res <= 5e-10
+    assert relerr(x, xo) <= 1e-7
+    lat.close()

@@ -113,3 +113,34 @@ def test_executable_protocol_and_outputs(tmp_path):
     rec = np.frombuffer(raw, dtype=np.dtype([("x", "<i4"), ("t", "<i4"), ("mu", "<i4"), ("re", "<f8"), ("im", "<f8")]))
     assert rec["x"][-1] == 15 and rec["t"][-1] == 23 and rec["mu"][-1] == 1
     assert np.abs(np.hypot(rec["re"], rec["im"]) - 1).max() < 1e-12     # links stay on the unit circle
+
+
+@pytest.mark.gpu
+def test_executable_forks_one_rank_per_gpu(tmp_path):
+    """ranks_x = 2: the binary forks a second rank itself (no mpirun), NCCL between the two GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _build(64, 64)
+    params = "2\n1\n0\n10\n0.5\n2\n20\n20\n0\n1\n"
+    env = dict(os.environ, SM_SEED="9", HOSTNAME="testhost")
+    r = subprocess.run([os.path.join(BIN, "SM_64x64")], input=params, capture_output=True, text=True, cwd=tmp_path,
+                       env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "* Total number of MPI ranks = 2" in r.stdout and "* Each rank has 2048 lattice sites" in r.stdout
+    sim = (tmp_path / "2D_U1_64x64_m00_SimData.txt").read_text().splitlines()
+    assert sim[7].split() == ["2", "1", "2"]
+    ep, acc = float(sim[-7].split()[0]), float(sim[-3])
+    assert 0.4 < ep < 0.9 and 0.0 < acc <= 1.0
+    confs = sorted(tmp_path.glob("2D_U1_Ns64_Nt64_b20000_m00000_*.ctxt"))
+    assert len(confs) == 20 and confs[0].stat().st_size == 2 * 4096 * 28
+    rec = np.frombuffer(confs[-1].read_bytes(),
+                        dtype=np.dtype([("x", "<i4"), ("t", "<i4"), ("mu", "<i4"), ("re", "<f8"), ("im", "<f8")]))
+    assert np.abs(np.hypot(rec["re"], rec["im"]) - 1).max() < 1e-12
+    # the gathered global field is consistent: its plaquette equals the measured one of the last configuration
+    U = (rec["re"] + 1j * rec["im"]).reshape(64 * 64, 2).T
+    import schwingermodel_b200 as sb
+    lat = sb.Lattice(64, 64)
+    _, sp, _ = lat.Compute_Plaquette01(np.ascontiguousarray(U), 2.0, want_field=False)
+    lat.close()
+    assert 0.3 < sp / 4096 < 0.95
