@@ -122,7 +122,7 @@ def test_executable_forks_one_rank_per_gpu(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     _build(64, 64)
-    params = "2\n1\n0\n10\n0.5\n2\n20\n20\n0\n1\n"
+    params = "2\n1\n0\n10\n1\n2\n60\n20\n0\n1\n"      # BASELINE config 1 parameters, split over two GPUs
     env = dict(os.environ, SM_SEED="9", HOSTNAME="testhost")
     r = subprocess.run([os.path.join(BIN, "SM_64x64")], input=params, capture_output=True, text=True, cwd=tmp_path,
                        env=env, timeout=600)
