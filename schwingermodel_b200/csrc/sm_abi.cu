@@ -176,6 +176,7 @@ struct sm_ctx {
     };
     std::vector<CgGraph> cg_graphs;
     bool use_graphs = true;
+    unsigned int attr_done = 0;   // kernel attributes already set on this context's device
     bool use_cluster = true;   // whole-solve resident kernels for small lattices (SM_CLUSTER_CG=0 disables)
     int coop_sites = -1;
     cplx* coop_hop = nullptr;
@@ -512,10 +513,9 @@ static int launch_fused(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, dou
     a.chunk_mode = 0;
     constexpr int STAGES = (MODE == FUSED_CG) ? 2 : 3;
     const size_t smem = fused_smem_bytes(MODE, STAGES, c->fus_block.x);
-    static bool attr_set = false;   // per instantiation
-    if (!attr_set) {
+    if (!(c->attr_done & (1u << MODE))) {   // function attributes are per device: once per context and instantiation
         CU(cudaFuncSetAttribute(k_dd_fused<MODE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
+        c->attr_done |= 1u << MODE;
     }
     bool split_launch = false;
     if (c->dist()) {
@@ -809,10 +809,9 @@ static int dev_cg_cluster(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, do
     TRY(resident_args(c, U, phi, x, m0, &a));
     int ctas = 1;
     while (ctas * kClusterThreads < c->V) ctas *= 2;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!(c->attr_done & (1u << 8))) {
         CU(cudaFuncSetAttribute(k_cg_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        attr_set = true;
+        c->attr_done |= 1u << 8;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ctas, 1, 1);
