@@ -344,7 +344,18 @@ def run_b200(args):
         apps += its + 2
     barrier()
     e2e_s = max(max_over_ranks(time.perf_counter() - t0), 1e-9)
+    # for transparency: ONE D_D_dagger_phi call through the host-buffer ABI (what the reference only does inside CG)
+    barrier()
+    t1 = time.perf_counter()
+    p_ = lambda r_: r_.ctypes.data_as(sb._abi.dp)   # noqa: E731
+    sb._abi.check(lat.lib.sm_D_D_dagger_phi(lat.ctx, p_(U_p[0]), p_(U_p[1]), p_(phi_p[0]), p_(phi_p[1]), p_(x_p[0]),
+                                            p_(x_p[1]), float(m0)))
+    barrier()
+    dd_call_s = max_over_ranks(time.perf_counter() - t1)
     e2e = {"value": apps * (L * L) / e2e_s, "unit": UNIT,
+           "single_dd_call": {"value": (L * L) / dd_call_s, "unit": UNIT, "seconds": dd_call_s,
+                              "note": "one sm_D_D_dagger_phi with host buffers: 96 B/site over PCIe for 192 B/site of "
+                                      "algorithmic work, i.e. bound by the host link, not by the GPU"},
            "h2d_bytes_per_step": int(N * 2 * U_p.nbytes), "d2h_bytes_per_step": int(N * x_p.nbytes),
            "call": "sm_conjugate_gradient (host buffers)", "solves": e2e_steps, "dd_applications": apps,
            "cg_converged": int(ok), "seconds": e2e_s, "solves_per_s": e2e_steps / e2e_s}

@@ -135,7 +135,6 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_fused(const FusedArgs a) {
     const bool col_active = (tid < a.cols_per_strip + 4) && (tc <= wt + 1);   // strip + 2 halo columns each side
     const bool col_owner = (tid >= 2) && (tid < a.cols_per_strip + 2) && (tc < wt);
     const double sR = (t == wt - 1) ? a.sR_edge : 1.0;
-    const double sL = (t == 0) ? a.sL_edge : 1.0;
     int chunk, xa, xb;
     if (a.chunk_mode == 0) {
         chunk = blockIdx.y;
@@ -158,11 +157,11 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_fused(const FusedArgs a) {
         for (int q = 0; q < STAGES * NARR; q++) s_stage[q * BT + tid] = zero;   // read back as zeros
     }
 
-    // stage row j: psi (or r, d_{k-1}, x) and the links of this thread's column
+    // stage row j (ring slot `slot`): psi (or r, d_{k-1}, x) and the links of this thread's column
     const bool split = (a.gU_lo != nullptr);
-    auto issue_row = [&](int j) {
+    auto issue_row = [&](int j, int slot) {
         if (col_active && j <= j_last) {
-            double2* st = s_stage + ((j - j_first) % STAGES) * NARR * BT + tid;
+            double2* st = s_stage + slot * NARR * BT + tid;
             const cplx *pU, *pin, *pr = nullptr;
             int cs;                                   // component stride of the source arrays
             if (split && j < 0) {
@@ -178,7 +177,10 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_fused(const FusedArgs a) {
                 pin = a.gin_hi + o;
                 if (MODE == FUSED_CG) pr = a.gr_hi + o;
             } else {
-                const int n = wrap_idx(j, wx) * wt + t;
+                int x = j;                            // -2 <= j <= wx+1: one correction wraps it
+                if (x < 0) x += wx;
+                else if (x >= wx) x -= wx;
+                const int n = x * wt + t;
                 cs = V;
                 pU = a.U + n;
                 pin = a.in + n;
@@ -206,88 +208,106 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_fused(const FusedArgs a) {
         cp_async_commit();
     };
 
-    // psi rows (m2 = j-2, m1 = j-1), t rows (t3 = j-3, t2 = j-2), links
-    cplx pm2_0 = zero, pm2_1 = zero, pm1_0 = zero, pm1_1 = zero;
-    cplx t3_0 = zero, t3_1 = zero, t2_0 = zero, t2_1 = zero;
-    cplx u0m2 = zero, u0m1 = zero, u1m3 = zero, u1m2 = zero, u1m1 = zero;
+    // Register rings, indexed with compile-time slots after the 6-fold unroll below (so a "rotation"
+    // costs no instruction):  P[.] psi rows j, j-1, j-2 ; Tr[.] t rows j-1, j-2 ; HX[.] the finished
+    // -x hop term conj(U1) proj(t) of the row below ; U0w/U1w links of rows j, j-1, j-2.
+    // The antiperiodic sign is folded into U0w when the row is taken (rt == 1: the +t hop out of column
+    // wt-1 and the -t hop into column 0 are the same link, so one factor serves both directions).
+    cplx P[3][2], Tr[2][2], HX[2], U0w[3], U1w[3];
+#pragma unroll
+    for (int q = 0; q < 3; q++) P[q][0] = P[q][1] = U0w[q] = U1w[q] = zero;
+#pragma unroll
+    for (int q = 0; q < 2; q++) Tr[q][0] = Tr[q][1] = HX[q] = zero;
     double acc[2] = {0.0, 0.0};
+    const double mass = a.mass;
 
 #pragma unroll
-    for (int q = 0; q < STAGES - 1; q++) issue_row(j_first + q);
+    for (int q = 0; q < STAGES - 1; q++) issue_row(j_first + q, q);
 
-    for (int j = j_first; j <= j_last; j++) {
-        issue_row(j + STAGES - 1);        // into the stage consumed at step j-1 (by this same thread)
-        cp_async_wait<STAGES - 1>();      // row j has landed; rows j+1 .. j+STAGES-1 may still fly
-        const double2* st = s_stage + ((j - j_first) % STAGES) * NARR * BT + tid;
-        const cplx v0 = st[0 * BT], v1 = st[1 * BT];
-        cplx p0 = st[2 * BT], p1 = st[3 * BT];
-        if (MODE == FUSED_CG && !first) {
-            // d_k = r_k + beta d_{k-1}  (conjugate_gradient.cpp:54-59), also at the halo sites
-            const cplx d0 = st[4 * BT], d1 = st[5 * BT];
-            p0 = make_double2(d0.x * beta + p0.x, d0.y * beta + p0.y);
-            p1 = make_double2(d1.x * beta + p1.x, d1.y * beta + p1.y);
-            if (col_owner && j >= xa && j < xb) {            // x += alpha_{k-1} d_{k-1}  (:34-36)
-                const int n = j * wt + t;
-                a.x[n] = cadd(st[6 * BT], cmul(alpha, d0));
-                a.x[V + n] = cadd(st[7 * BT], cmul(alpha, d1));
-            }
-        }
-        if (MODE == FUSED_CG && col_owner) {
-            if (j >= xa && j < xb) {
-                const int n = j * wt + t;
-                a.d_new[n] = p0;
-                a.d_new[V + n] = p1;
-            } else if (split && j < 0) {             // keep d_k's ghost rows for the next iteration
-                a.gd_lo[(j + 2) * wt + t] = p0;
-                a.gd_lo[2 * wt + (j + 2) * wt + t] = p1;
-            } else if (split && j >= wx) {
-                a.gd_hi[(j - wx) * wt + t] = p0;
-                a.gd_hi[2 * wt + (j - wx) * wt + t] = p1;
-            }
-        }
+    for (int jb = j_first; jb <= j_last; jb += 6) {
+#pragma unroll
+        for (int s = 0; s < 6; s++) {
+            const int j = jb + s;
+            if (j > j_last) break;                         // uniform over the block
+            constexpr int kUnused = 0;
+            (void)kUnused;
+            const int c = s % 3, m1 = (s + 2) % 3, m2 = (s + 1) % 3;   // ring slots of rows j, j-1, j-2
+            const int tn_i = s % 2, t2_i = (s + 1) % 2;
 
-        // publish the t-direction half-spinors of psi row j-1 (for D^dagger) and t row j-2 (for D)
-        double2* line = s_line + (j & 1) * 4 * BT;
-        line[0 * BT + tid] = Hop<true>::from_tp(pm1_0, pm1_1);                    // read by column t-1
-        line[1 * BT + tid] = cmulc(u0m1, Hop<true>::from_tm(pm1_0, pm1_1));      // read by column t+1
-        line[2 * BT + tid] = Hop<false>::from_tp(t2_0, t2_1);
-        line[3 * BT + tid] = cmulc(u0m2, Hop<false>::from_tm(t2_0, t2_1));
-        __syncthreads();
-
-        // t(j-1) = D^dagger psi at row j-1
-        cplx tn0, tn1;
-        {
-            cplx a0, a1;
-            Hop<true>::add_tp(cscale(sR, cmul(u0m1, line[0 * BT + tr])), a0, a1);
-            Hop<true>::add_xp(cmul(u1m1, Hop<true>::from_xp(p0, p1)), a0, a1);
-            Hop<true>::add_tm(cscale(sL, line[1 * BT + tl]), a0, a1);
-            Hop<true>::add_xm(cmulc(u1m2, Hop<true>::from_xm(pm2_0, pm2_1)), a0, a1);
-            tn0 = make_double2(a.mass * pm1_0.x - 0.5 * a0.x, a.mass * pm1_0.y - 0.5 * a0.y);
-            tn1 = make_double2(a.mass * pm1_1.x - 0.5 * a1.x, a.mass * pm1_1.y - 0.5 * a1.y);
-        }
-        // out(j-2) = D t at row j-2
-        if (j >= xa + 2 && col_owner) {
-            cplx a0, a1;
-            Hop<false>::add_tp(cscale(sR, cmul(u0m2, line[2 * BT + tr])), a0, a1);
-            Hop<false>::add_xp(cmul(u1m2, Hop<false>::from_xp(tn0, tn1)), a0, a1);
-            Hop<false>::add_tm(cscale(sL, line[3 * BT + tl]), a0, a1);
-            Hop<false>::add_xm(cmulc(u1m3, Hop<false>::from_xm(t3_0, t3_1)), a0, a1);
-            const cplx o0 = make_double2(a.mass * t2_0.x - 0.5 * a0.x, a.mass * t2_0.y - 0.5 * a0.y);
-            const cplx o1 = make_double2(a.mass * t2_1.x - 0.5 * a1.x, a.mass * t2_1.y - 0.5 * a1.y);
-            const int n = (j - 2) * wt + t;      // xa <= j-2 < xb: no wrap
-            st_stream(a.out + n, o0);
-            st_stream(a.out + V + n, o1);
-            if (MODE != FUSED_PLAIN) {           // dot(psi, out) = sum psi conj(out)
-                const cplx q0 = cmul_conj(pm2_0, o0), q1 = cmul_conj(pm2_1, o1);
-                acc[0] += q0.x + q1.x;
-                acc[1] += q0.y + q1.y;
+            issue_row(j + STAGES - 1, (s + STAGES - 1) % STAGES);   // into the stage consumed at step j-1
+            cp_async_wait<STAGES - 1>();                            // row j has landed
+            const double2* st = s_stage + (s % STAGES) * NARR * BT + tid;
+            U0w[c] = cscale(sR, st[0 * BT]);
+            U1w[c] = st[1 * BT];
+            cplx p0 = st[2 * BT], p1 = st[3 * BT];
+            if (MODE == FUSED_CG && !first) {
+                // d_k = r_k + beta d_{k-1}  (conjugate_gradient.cpp:54-59), also at the halo sites
+                const cplx d0 = st[4 * BT], d1 = st[5 * BT];
+                p0 = make_double2(d0.x * beta + p0.x, d0.y * beta + p0.y);
+                p1 = make_double2(d1.x * beta + p1.x, d1.y * beta + p1.y);
+                if (col_owner && j >= xa && j < xb) {            // x += alpha_{k-1} d_{k-1}  (:34-36)
+                    const int n = j * wt + t;
+                    a.x[n] = cadd(st[6 * BT], cmul(alpha, d0));
+                    a.x[V + n] = cadd(st[7 * BT], cmul(alpha, d1));
+                }
             }
+            if (MODE == FUSED_CG && col_owner) {
+                if (j >= xa && j < xb) {
+                    const int n = j * wt + t;
+                    a.d_new[n] = p0;
+                    a.d_new[V + n] = p1;
+                } else if (split && j < 0) {             // keep d_k's ghost rows for the next iteration
+                    a.gd_lo[(j + 2) * wt + t] = p0;
+                    a.gd_lo[2 * wt + (j + 2) * wt + t] = p1;
+                } else if (split && j >= wx) {
+                    a.gd_hi[(j - wx) * wt + t] = p0;
+                    a.gd_hi[2 * wt + (j - wx) * wt + t] = p1;
+                }
+            }
+            P[c][0] = p0;
+            P[c][1] = p1;
+
+            // publish the t-direction half-spinors of psi row j-1 (for D^dagger) and t row j-2 (for D)
+            double2* line = s_line + (s & 1) * 4 * BT;
+            line[0 * BT + tid] = Hop<true>::from_tp(P[m1][0], P[m1][1]);                       // read by column t-1
+            line[1 * BT + tid] = cmulc(U0w[m1], Hop<true>::from_tm(P[m1][0], P[m1][1]));       // read by column t+1
+            line[2 * BT + tid] = Hop<false>::from_tp(Tr[t2_i][0], Tr[t2_i][1]);
+            line[3 * BT + tid] = cmulc(U0w[m2], Hop<false>::from_tm(Tr[t2_i][0], Tr[t2_i][1]));
+            __syncthreads();
+
+            // t(j-1) = D^dagger psi at row j-1
+            cplx tn0, tn1;
+            {
+                cplx a0, a1;
+                Hop<true>::add_tp(cmul(U0w[m1], line[0 * BT + tr]), a0, a1);
+                Hop<true>::add_xp(cmul(U1w[m1], Hop<true>::from_xp(p0, p1)), a0, a1);
+                Hop<true>::add_tm(line[1 * BT + tl], a0, a1);
+                Hop<true>::add_xm(cmulc(U1w[m2], Hop<true>::from_xm(P[m2][0], P[m2][1])), a0, a1);
+                tn0 = make_double2(mass * P[m1][0].x - 0.5 * a0.x, mass * P[m1][0].y - 0.5 * a0.y);
+                tn1 = make_double2(mass * P[m1][1].x - 0.5 * a1.x, mass * P[m1][1].y - 0.5 * a1.y);
+            }
+            // out(j-2) = D t at row j-2
+            if (j >= xa + 2 && col_owner) {
+                cplx a0, a1;
+                Hop<false>::add_tp(cmul(U0w[m2], line[2 * BT + tr]), a0, a1);
+                Hop<false>::add_xp(cmul(U1w[m2], Hop<false>::from_xp(tn0, tn1)), a0, a1);
+                Hop<false>::add_tm(line[3 * BT + tl], a0, a1);
+                Hop<false>::add_xm(HX[tn_i], a0, a1);             // conj(U1) proj(t) of row j-3, finished at step j-2
+                const cplx o0 = make_double2(mass * Tr[t2_i][0].x - 0.5 * a0.x, mass * Tr[t2_i][0].y - 0.5 * a0.y);
+                const cplx o1 = make_double2(mass * Tr[t2_i][1].x - 0.5 * a1.x, mass * Tr[t2_i][1].y - 0.5 * a1.y);
+                const int n = (j - 2) * wt + t;      // xa <= j-2 < xb: no wrap
+                st_stream(a.out + n, o0);
+                st_stream(a.out + V + n, o1);
+                if (MODE != FUSED_PLAIN) {           // dot(psi, out) = sum psi conj(out)
+                    const cplx q0 = cmul_conj(P[m2][0], o0), q1 = cmul_conj(P[m2][1], o1);
+                    acc[0] += q0.x + q1.x;
+                    acc[1] += q0.y + q1.y;
+                }
+            }
+            HX[tn_i] = cmulc(U1w[m1], Hop<false>::from_xm(tn0, tn1));   // -x hop term that out(row j) takes at step j+2
+            Tr[tn_i][0] = tn0;
+            Tr[tn_i][1] = tn1;
         }
-        // rotate the windows
-        t3_0 = t2_0; t3_1 = t2_1; t2_0 = tn0; t2_1 = tn1;
-        pm2_0 = pm1_0; pm2_1 = pm1_1; pm1_0 = p0; pm1_1 = p1;
-        u1m3 = u1m2; u1m2 = u1m1; u1m1 = v1;
-        u0m2 = u0m1; u0m1 = v0;
     }
 
     if (MODE != FUSED_PLAIN) {
