@@ -72,6 +72,13 @@ SM_API const char* sm_last_error(void);
 SM_API int sm_local_dims(const sm_ctx* ctx, int dims[4]);
 /* CG controls = the reference's mutable globals CG::tol / CG::max_iter (src/variables.cpp:35-38) */
 SM_API int sm_set_cg(sm_ctx* ctx, double tol, int max_iter);
+/* Solver used by every CG of the context (conjugate_gradient, HMC::Force, HMC::Action):
+ *   SM_SOLVER_REFERENCE  the reference's algorithm in double precision (default; dH parity <= 1e-8)
+ *   SM_SOLVER_MIXED      opt-in: single-precision inner CG inside a double-precision defect correction
+ *                        (lattices above ~75k sites on a single tile); same stopping criterion, checked on the
+ *                        TRUE residual, but a different iterate than the reference's */
+enum { SM_SOLVER_REFERENCE = 0, SM_SOLVER_MIXED = 1 };
+SM_API int sm_set_solver(sm_ctx* ctx, int solver);
 /* device time (ms) of the last sm_* call on this context, measured with CUDA events on the
  * context's stream around the kernels only (no copies) */
 SM_API int sm_last_kernel_ms(const sm_ctx* ctx, double* ms);

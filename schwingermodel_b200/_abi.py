@@ -17,6 +17,7 @@ HEADER_PATH = os.path.join(ROOT, "include", "schwinger_b200.h")
 SM_OK, SM_ERR_ARG, SM_ERR_CUDA, SM_ERR_NCCL, SM_ERR_IO, SM_ERR_STATE = range(6)
 SM_NCCL_ID_BYTES = 128
 SM_P2P_HANDLE_BYTES = 64
+SM_SOLVER_REFERENCE, SM_SOLVER_MIXED = 0, 1
 
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int)
@@ -58,6 +59,7 @@ _SIGS = {
     "sm_destroy": [ctx_p],
     "sm_local_dims": [ctx_p, ip],
     "sm_set_cg": [ctx_p, C.c_double, C.c_int],
+    "sm_set_solver": [ctx_p, C.c_int],
     "sm_last_kernel_ms": [ctx_p, dp],
     "sm_launch_count": [ctx_p, C.POINTER(C.c_longlong)],
     "sm_one_pass_dd": [ctx_p, ip],

@@ -23,6 +23,27 @@ __device__ __forceinline__ cplx cdiv(cplx a, cplx b) {
     return make_double2((a.x * b.x + a.y * b.y) * inv, (a.y * b.x - a.x * b.y) * inv);
 }
 
+// single-precision twins (the opt-in mixed-precision solver stores its inner vectors as float2)
+typedef float2 cplxf;
+__device__ __forceinline__ cplxf cmul(cplxf a, cplxf b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ cplxf cmulc(cplxf a, cplxf b) { return make_float2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ cplxf cmul_conj(cplxf a, cplxf b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }
+__device__ __forceinline__ cplxf cadd(cplxf a, cplxf b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cplxf csub(cplxf a, cplxf b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cplxf cscale(float s, cplxf a) { return make_float2(s * a.x, s * a.y); }
+
+// scalar type of a complex type, and a constructor that works for both
+template <typename C> struct RealOf;
+template <> struct RealOf<cplx> { typedef double type; };
+template <> struct RealOf<cplxf> { typedef float type; };
+template <typename C>
+__device__ __forceinline__ C mkc(typename RealOf<C>::type x, typename RealOf<C>::type y) {
+    C r;
+    r.x = x;
+    r.y = y;
+    return r;
+}
+
 // 16-byte global accesses.  Streaming data that no other thread of the SM re-reads goes past L1.
 __device__ __forceinline__ cplx ldg(const cplx* p) { return __ldg(p); }
 __device__ __forceinline__ cplx ld_stream(const cplx* p) {
@@ -32,6 +53,15 @@ __device__ __forceinline__ cplx ld_stream(const cplx* p) {
 }
 __device__ __forceinline__ void st_stream(cplx* p, cplx v) {
     asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+
+__device__ __forceinline__ cplxf ld_stream(const cplxf* p) {
+    cplxf r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream(cplxf* p, cplxf v) {
+    asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
 }
 
 constexpr int kBlock = 256;          // threads per block for every kernel

@@ -24,10 +24,11 @@ namespace sm {
 
 enum { FUSED_PLAIN = 0, FUSED_DOT = 1, FUSED_CG = 2 };
 
-struct FusedArgs {
-    const cplx* U;
-    const cplx* in;      // psi (PLAIN/DOT) or d_{k-1} (CG)
-    cplx* out;           // D D^dagger psi  (A d_k in CG)
+template <typename C>
+struct FusedArgsT {
+    const C* U;
+    const C* in;      // psi (PLAIN/DOT) or d_{k-1} (CG)
+    C* out;           // D D^dagger psi  (A d_k in CG)
     int wx, wt, V;
     int rows_per_block;
     int cols_per_strip;  // output columns per block (<= blockDim.x - 4)
@@ -41,38 +42,40 @@ struct FusedArgs {
     double* sums_out;
     // CG mode
     CgState* st;
-    const cplx* r;       // r_k
-    cplx* x;             // x_{k-1} -> x_k
-    cplx* d_new;         // d_k
+    const C* r;       // r_k
+    C* x;             // x_{k-1} -> x_k
+    C* d_new;         // d_k
     int first;           // iteration 0: d_0 = r_0, no x update owed
     int cur;             // parity of the iteration (selects rr[], the d ping-pong is in the pointers)
     double tol;
     // lattice split along x (ranks_t == 1): rows -2,-1 ("lo") and wx, wx+1 ("hi") live in ghost
     // arrays laid out [component][2 rows][wt]; null = wrap inside the tile
-    const cplx* gU_lo;
-    const cplx* gU_hi;
-    const cplx* gin_lo;   // ghost rows of `in`
-    const cplx* gin_hi;
-    const cplx* gr_lo;    // CG: ghost rows of r
-    const cplx* gr_hi;
-    cplx* gd_lo;          // CG: ghost rows of d_k, written here for the next iteration
-    cplx* gd_hi;
+    const C* gU_lo;
+    const C* gU_hi;
+    const C* gin_lo;   // ghost rows of `in`
+    const C* gin_hi;
+    const C* gr_lo;    // CG: ghost rows of r
+    const C* gr_hi;
+    C* gd_lo;          // CG: ghost rows of d_k, written here for the next iteration
+    C* gd_hi;
 };
+
+typedef FusedArgsT<cplx> FusedArgs;
 
 // hop algebra shared by both operators: s = +1 for D^dagger, -1 for D (see k_wilson)
 template <bool DAG>
 struct Hop {
-    static constexpr double s = DAG ? 1.0 : -1.0;
+    static constexpr int si = DAG ? 1 : -1;
     // half-spinors as seen from the receiving site
-    static __device__ __forceinline__ cplx from_tp(cplx p0, cplx p1) { return make_double2(p0.x + s * p1.x, p0.y + s * p1.y); }
-    static __device__ __forceinline__ cplx from_xp(cplx p0, cplx p1) { return make_double2(p0.x + s * p1.y, p0.y - s * p1.x); }
-    static __device__ __forceinline__ cplx from_tm(cplx p0, cplx p1) { return make_double2(p0.x - s * p1.x, p0.y - s * p1.y); }
-    static __device__ __forceinline__ cplx from_xm(cplx p0, cplx p1) { return make_double2(p0.x - s * p1.y, p0.y + s * p1.x); }
+    template <typename C> static __device__ __forceinline__ C from_tp(C p0, C p1) { const typename RealOf<C>::type s = si; return mkc<C>(p0.x + s * p1.x, p0.y + s * p1.y); }
+    template <typename C> static __device__ __forceinline__ C from_xp(C p0, C p1) { const typename RealOf<C>::type s = si; return mkc<C>(p0.x + s * p1.y, p0.y - s * p1.x); }
+    template <typename C> static __device__ __forceinline__ C from_tm(C p0, C p1) { const typename RealOf<C>::type s = si; return mkc<C>(p0.x - s * p1.x, p0.y - s * p1.y); }
+    template <typename C> static __device__ __forceinline__ C from_xm(C p0, C p1) { const typename RealOf<C>::type s = si; return mkc<C>(p0.x - s * p1.y, p0.y + s * p1.x); }
     // accumulate the four hop terms v (already multiplied by the link and the sign)
-    static __device__ __forceinline__ void add_tp(cplx v, cplx& a0, cplx& a1) { a0 = v; a1 = cscale(s, v); }
-    static __device__ __forceinline__ void add_xp(cplx v, cplx& a0, cplx& a1) { a0 = cadd(a0, v); a1.x -= s * v.y; a1.y += s * v.x; }
-    static __device__ __forceinline__ void add_tm(cplx v, cplx& a0, cplx& a1) { a0 = cadd(a0, v); a1.x -= s * v.x; a1.y -= s * v.y; }
-    static __device__ __forceinline__ void add_xm(cplx v, cplx& a0, cplx& a1) { a0 = cadd(a0, v); a1.x += s * v.y; a1.y -= s * v.x; }
+    template <typename C> static __device__ __forceinline__ void add_tp(C v, C& a0, C& a1) { const typename RealOf<C>::type s = si; a0 = v; a1 = cscale(s, v); }
+    template <typename C> static __device__ __forceinline__ void add_xp(C v, C& a0, C& a1) { const typename RealOf<C>::type s = si; a0 = cadd(a0, v); a1.x -= s * v.y; a1.y += s * v.x; }
+    template <typename C> static __device__ __forceinline__ void add_tm(C v, C& a0, C& a1) { const typename RealOf<C>::type s = si; a0 = cadd(a0, v); a1.x -= s * v.x; a1.y -= s * v.y; }
+    template <typename C> static __device__ __forceinline__ void add_xm(C v, C& a0, C& a1) { const typename RealOf<C>::type s = si; a0 = cadd(a0, v); a1.x += s * v.y; a1.y -= s * v.x; }
 };
 
 __device__ __forceinline__ int wrap_idx(int a, int n) {
@@ -85,6 +88,12 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
     const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
 }
+// one field element: 16 bytes (double complex, L1 bypassed) or 8 bytes (single complex)
+__device__ __forceinline__ void cp_async_elem(cplx* smem_dst, const cplx* gmem_src) { cp_async16(smem_dst, gmem_src); }
+__device__ __forceinline__ void cp_async_elem(cplxf* smem_dst, const cplxf* gmem_src) {
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -92,32 +101,34 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 __host__ __device__ constexpr int fused_arrays(int mode) { return mode == FUSED_CG ? 8 : 4; }
-constexpr size_t fused_smem_bytes(int mode, int stages, int BT) {
-    return sizeof(cplx) * (size_t)BT * (2 * 4 + (size_t)stages * fused_arrays(mode));
+constexpr size_t fused_smem_bytes(int mode, int stages, int BT, size_t elem_bytes = sizeof(cplx)) {
+    return elem_bytes * (size_t)BT * (2 * 4 + (size_t)stages * fused_arrays(mode));
 }
 
 // Shared memory:  line  [2 parities][4][BT]   t-direction half-spinors of the psi row and the t row
 //                 stage [STAGES][NARR][BT]    rows in flight (each thread stages its own column:
 //                                             cp.async, no block barrier needed for it)
-template <int MODE, int STAGES>
-__global__ void __launch_bounds__(kBlock, 2) k_dd_fused(const FusedArgs a) {
-    extern __shared__ double2 s_mem[];
+template <typename C, int MODE, int STAGES>
+__global__ void __launch_bounds__(kBlock, 2) k_dd_fused(const FusedArgsT<C> a) {
+    typedef typename RealOf<C>::type R;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    C* const s_mem = reinterpret_cast<C*>(s_raw);
     constexpr int NARR = fused_arrays(MODE);
     const int BT = blockDim.x;
     const int tid = threadIdx.x;
     const int wt = a.wt, wx = a.wx, V = a.V;
-    double2* const s_line = s_mem;
-    double2* const s_stage = s_mem + 2 * 4 * BT;
+    C* const s_line = s_mem;
+    C* const s_stage = s_mem + 2 * 4 * BT;
 
-    double beta = 0.0;
-    cplx alpha = make_double2(0.0, 0.0);
+    R beta = 0;
+    C alpha = mkc<C>(0, 0);
     bool first = true;
     if (MODE == FUSED_CG) {
         if (a.st->done) return;
         const int cur = a.cur;
         first = (a.first != 0);
         if (!first) {
-            if (cg_converged(a.st, cur, a.tol)) {
+            if (cg_converged(a.st, cur, a.st->tol)) {
                 if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0 && a.chunk_mode != 1) {
                     a.st->iters = a.st->k - 1;
                     a.st->converged = 1;
@@ -125,8 +136,8 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_fused(const FusedArgs a) {
                 }
                 return;
             }
-            beta = a.st->rr[cur] / a.st->rr[cur ^ 1];
-            alpha = make_double2(a.st->alpha[0], a.st->alpha[1]);
+            beta = (R)(a.st->rr[cur] / a.st->rr[cur ^ 1]);
+            alpha = mkc<C>((R)a.st->alpha[0], (R)a.st->alpha[1]);
         }
     }
 
@@ -134,7 +145,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_fused(const FusedArgs a) {
     const int t = wrap_idx(tc, wt);
     const bool col_active = (tid < a.cols_per_strip + 4) && (tc <= wt + 1);   // strip + 2 halo columns each side
     const bool col_owner = (tid >= 2) && (tid < a.cols_per_strip + 2) && (tc < wt);
-    const double sR = (t == wt - 1) ? a.sR_edge : 1.0;
+    const R sR = (R)((t == wt - 1) ? a.sR_edge : 1.0);
     int chunk, xa, xb;
     if (a.chunk_mode == 0) {
         chunk = blockIdx.y;
@@ -152,7 +163,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_fused(const FusedArgs a) {
     const int tl = (tid == 0) ? 0 : tid - 1, tr = (tid == BT - 1) ? tid : tid + 1;
     const int j_first = xa - 2, j_last = xb + 1;
 
-    const cplx zero = make_double2(0.0, 0.0);
+    const C zero = mkc<C>(0, 0);
     if (!col_active) {
         for (int q = 0; q < STAGES * NARR; q++) s_stage[q * BT + tid] = zero;   // read back as zeros
     }
@@ -161,8 +172,8 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_fused(const FusedArgs a) {
     const bool split = (a.gU_lo != nullptr);
     auto issue_row = [&](int j, int slot) {
         if (col_active && j <= j_last) {
-            double2* st = s_stage + slot * NARR * BT + tid;
-            const cplx *pU, *pin, *pr = nullptr;
+            C* st = s_stage + slot * NARR * BT + tid;
+            const C *pU, *pin, *pr = nullptr;
             int cs;                                   // component stride of the source arrays
             if (split && j < 0) {
                 const int o = (j + 2) * wt + t;
@@ -186,21 +197,21 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_fused(const FusedArgs a) {
                 pin = a.in + n;
                 if (MODE == FUSED_CG) pr = a.r + n;
             }
-            cp_async16(st + 0 * BT, pU);
-            cp_async16(st + 1 * BT, pU + cs);
+            cp_async_elem(st + 0 * BT, pU);
+            cp_async_elem(st + 1 * BT, pU + cs);
             if (MODE != FUSED_CG) {
-                cp_async16(st + 2 * BT, pin);
-                cp_async16(st + 3 * BT, pin + cs);
+                cp_async_elem(st + 2 * BT, pin);
+                cp_async_elem(st + 3 * BT, pin + cs);
             } else {
-                cp_async16(st + 2 * BT, pr);
-                cp_async16(st + 3 * BT, pr + cs);
+                cp_async_elem(st + 2 * BT, pr);
+                cp_async_elem(st + 3 * BT, pr + cs);
                 if (!first) {
-                    cp_async16(st + 4 * BT, pin);
-                    cp_async16(st + 5 * BT, pin + cs);
+                    cp_async_elem(st + 4 * BT, pin);
+                    cp_async_elem(st + 5 * BT, pin + cs);
                     if (col_owner && j >= xa && j < xb) {
                         const int n = j * wt + t;
-                        cp_async16(st + 6 * BT, a.x + n);
-                        cp_async16(st + 7 * BT, a.x + V + n);
+                        cp_async_elem(st + 6 * BT, a.x + n);
+                        cp_async_elem(st + 7 * BT, a.x + V + n);
                     }
                 }
             }
@@ -213,13 +224,13 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_fused(const FusedArgs a) {
     // -x hop term conj(U1) proj(t) of the row below ; U0w/U1w links of rows j, j-1, j-2.
     // The antiperiodic sign is folded into U0w when the row is taken (rt == 1: the +t hop out of column
     // wt-1 and the -t hop into column 0 are the same link, so one factor serves both directions).
-    cplx P[3][2], Tr[2][2], HX[2], U0w[3], U1w[3];
+    C P[3][2], Tr[2][2], HX[2], U0w[3], U1w[3];
 #pragma unroll
     for (int q = 0; q < 3; q++) P[q][0] = P[q][1] = U0w[q] = U1w[q] = zero;
 #pragma unroll
     for (int q = 0; q < 2; q++) Tr[q][0] = Tr[q][1] = HX[q] = zero;
     double acc[2] = {0.0, 0.0};
-    const double mass = a.mass;
+    const R mass = (R)a.mass, half = (R)0.5;
 
 #pragma unroll
     for (int q = 0; q < STAGES - 1; q++) issue_row(j_first + q, q);
@@ -236,15 +247,15 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_fused(const FusedArgs a) {
 
             issue_row(j + STAGES - 1, (s + STAGES - 1) % STAGES);   // into the stage consumed at step j-1
             cp_async_wait<STAGES - 1>();                            // row j has landed
-            const double2* st = s_stage + (s % STAGES) * NARR * BT + tid;
+            const C* st = s_stage + (s % STAGES) * NARR * BT + tid;
             U0w[c] = cscale(sR, st[0 * BT]);
             U1w[c] = st[1 * BT];
-            cplx p0 = st[2 * BT], p1 = st[3 * BT];
+            C p0 = st[2 * BT], p1 = st[3 * BT];
             if (MODE == FUSED_CG && !first) {
                 // d_k = r_k + beta d_{k-1}  (conjugate_gradient.cpp:54-59), also at the halo sites
-                const cplx d0 = st[4 * BT], d1 = st[5 * BT];
-                p0 = make_double2(d0.x * beta + p0.x, d0.y * beta + p0.y);
-                p1 = make_double2(d1.x * beta + p1.x, d1.y * beta + p1.y);
+                const C d0 = st[4 * BT], d1 = st[5 * BT];
+                p0 = mkc<C>(d0.x * beta + p0.x, d0.y * beta + p0.y);
+                p1 = mkc<C>(d1.x * beta + p1.x, d1.y * beta + p1.y);
                 if (col_owner && j >= xa && j < xb) {            // x += alpha_{k-1} d_{k-1}  (:34-36)
                     const int n = j * wt + t;
                     a.x[n] = cadd(st[6 * BT], cmul(alpha, d0));
@@ -268,7 +279,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_fused(const FusedArgs a) {
             P[c][1] = p1;
 
             // publish the t-direction half-spinors of psi row j-1 (for D^dagger) and t row j-2 (for D)
-            double2* line = s_line + (s & 1) * 4 * BT;
+            C* line = s_line + (s & 1) * 4 * BT;
             line[0 * BT + tid] = Hop<true>::from_tp(P[m1][0], P[m1][1]);                       // read by column t-1
             line[1 * BT + tid] = cmulc(U0w[m1], Hop<true>::from_tm(P[m1][0], P[m1][1]));       // read by column t+1
             line[2 * BT + tid] = Hop<false>::from_tp(Tr[t2_i][0], Tr[t2_i][1]);
@@ -276,32 +287,32 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_fused(const FusedArgs a) {
             __syncthreads();
 
             // t(j-1) = D^dagger psi at row j-1
-            cplx tn0, tn1;
+            C tn0, tn1;
             {
-                cplx a0, a1;
+                C a0, a1;
                 Hop<true>::add_tp(cmul(U0w[m1], line[0 * BT + tr]), a0, a1);
                 Hop<true>::add_xp(cmul(U1w[m1], Hop<true>::from_xp(p0, p1)), a0, a1);
                 Hop<true>::add_tm(line[1 * BT + tl], a0, a1);
                 Hop<true>::add_xm(cmulc(U1w[m2], Hop<true>::from_xm(P[m2][0], P[m2][1])), a0, a1);
-                tn0 = make_double2(mass * P[m1][0].x - 0.5 * a0.x, mass * P[m1][0].y - 0.5 * a0.y);
-                tn1 = make_double2(mass * P[m1][1].x - 0.5 * a1.x, mass * P[m1][1].y - 0.5 * a1.y);
+                tn0 = mkc<C>(mass * P[m1][0].x - half * a0.x, mass * P[m1][0].y - half * a0.y);
+                tn1 = mkc<C>(mass * P[m1][1].x - half * a1.x, mass * P[m1][1].y - half * a1.y);
             }
             // out(j-2) = D t at row j-2
             if (j >= xa + 2 && col_owner) {
-                cplx a0, a1;
+                C a0, a1;
                 Hop<false>::add_tp(cmul(U0w[m2], line[2 * BT + tr]), a0, a1);
                 Hop<false>::add_xp(cmul(U1w[m2], Hop<false>::from_xp(tn0, tn1)), a0, a1);
                 Hop<false>::add_tm(line[3 * BT + tl], a0, a1);
                 Hop<false>::add_xm(HX[tn_i], a0, a1);             // conj(U1) proj(t) of row j-3, finished at step j-2
-                const cplx o0 = make_double2(mass * Tr[t2_i][0].x - 0.5 * a0.x, mass * Tr[t2_i][0].y - 0.5 * a0.y);
-                const cplx o1 = make_double2(mass * Tr[t2_i][1].x - 0.5 * a1.x, mass * Tr[t2_i][1].y - 0.5 * a1.y);
+                const C o0 = mkc<C>(mass * Tr[t2_i][0].x - half * a0.x, mass * Tr[t2_i][0].y - half * a0.y);
+                const C o1 = mkc<C>(mass * Tr[t2_i][1].x - half * a1.x, mass * Tr[t2_i][1].y - half * a1.y);
                 const int n = (j - 2) * wt + t;      // xa <= j-2 < xb: no wrap
                 st_stream(a.out + n, o0);
                 st_stream(a.out + V + n, o1);
                 if (MODE != FUSED_PLAIN) {           // dot(psi, out) = sum psi conj(out)
-                    const cplx q0 = cmul_conj(P[m2][0], o0), q1 = cmul_conj(P[m2][1], o1);
-                    acc[0] += q0.x + q1.x;
-                    acc[1] += q0.y + q1.y;
+                    const C q0 = cmul_conj(P[m2][0], o0), q1 = cmul_conj(P[m2][1], o1);
+                    acc[0] += (double)q0.x + (double)q1.x;
+                    acc[1] += (double)q0.y + (double)q1.y;
                 }
             }
             HX[tn_i] = cmulc(U1w[m1], Hop<false>::from_xm(tn0, tn1));   // -x hop term that out(row j) takes at step j+2
@@ -321,19 +332,22 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_fused(const FusedArgs a) {
 }
 
 // r -= alpha A d ; |r|^2 ; alpha kept for the x update that the next fused pass applies
-__global__ void __launch_bounds__(kBlock) k_cg_resid(CgState* st, int cur, cplx* __restrict__ r,
-                                                     const cplx* __restrict__ Ad, int n_elems, double* partials,
-                                                     unsigned int* ticket, double* sums_out) {
+template <typename C>
+__global__ void __launch_bounds__(kBlock) k_cg_resid(CgState* st, int cur, C* __restrict__ r, const C* __restrict__ Ad,
+                                                     int n_elems, double* partials, unsigned int* ticket,
+                                                     double* sums_out) {
+    typedef typename RealOf<C>::type R;
     if (st->done) return;
     const cplx alpha = cdiv(make_double2(st->rr[cur], 0.0), make_double2(st->dAd[0], st->dAd[1]));
+    const C al = mkc<C>((R)alpha.x, (R)alpha.y);
     double acc[1] = {0.0};
     const int stride = gridDim.x * blockDim.x;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += stride) {
-        const cplx av = ld_stream(Ad + i);
-        cplx rv = r[i];
-        rv = csub(rv, cmul(alpha, av));
+        const C av = ld_stream(Ad + i);
+        C rv = r[i];
+        rv = csub(rv, cmul(al, av));
         r[i] = rv;
-        acc[0] += rv.x * rv.x + rv.y * rv.y;
+        acc[0] += (double)rv.x * rv.x + (double)rv.y * rv.y;
     }
     if (grid_reduce<1>(acc, partials, ticket)) {
         if (threadIdx.x == 0) {
@@ -348,15 +362,73 @@ __global__ void __launch_bounds__(kBlock) k_cg_resid(CgState* st, int cur, cplx*
 }
 
 // the x update the loop still owes when it stops: x += alpha_K d_K
-__global__ void __launch_bounds__(kBlock) k_cg_flush_x(CgState* st, cplx* __restrict__ x, const cplx* __restrict__ d_buf0,
-                                                       const cplx* __restrict__ d_buf1, int n_elems) {
+template <typename C>
+__global__ void __launch_bounds__(kBlock) k_cg_flush_x(CgState* st, C* __restrict__ x, const C* __restrict__ d_buf0,
+                                                       const C* __restrict__ d_buf1, int n_elems) {
+    typedef typename RealOf<C>::type R;
     if (!st->pending) return;
-    const cplx alpha = make_double2(st->alpha[0], st->alpha[1]);
-    const cplx* __restrict__ d = st->pending_buf ? d_buf1 : d_buf0;
+    const C alpha = mkc<C>((R)st->alpha[0], (R)st->alpha[1]);
+    const C* __restrict__ d = st->pending_buf ? d_buf1 : d_buf0;
     const int stride = gridDim.x * blockDim.x;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += stride) {
         x[i] = cadd(x[i], cmul(alpha, ld_stream(d + i)));
     }
+}
+
+// ---- opt-in mixed-precision solver: single-precision inner CG inside a double-precision defect correction ----
+__global__ void __launch_bounds__(kBlock) k_to_single(const cplx* __restrict__ in, cplxf* __restrict__ out, int n_elems) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += stride) {
+        const cplx v = ld_stream(in + i);
+        out[i] = make_float2((float)v.x, (float)v.y);
+    }
+}
+
+// r = phi - A x (true residual, double) ; r32 = r ; e32 = 0 ; sums: |phi|^2, |r|^2
+__global__ void __launch_bounds__(kBlock) k_mixed_residual(const cplx* __restrict__ phi, const cplx* __restrict__ Ax,
+                                                           cplxf* __restrict__ r32, cplxf* __restrict__ e32, int n_elems,
+                                                           double* partials, unsigned int* ticket, double* sums_out) {
+    double acc[2] = {0.0, 0.0};
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += stride) {
+        const cplx f = ld_stream(phi + i), a = ld_stream(Ax + i);
+        const cplx r = csub(f, a);
+        r32[i] = make_float2((float)r.x, (float)r.y);
+        e32[i] = make_float2(0.f, 0.f);
+        acc[0] += f.x * f.x + f.y * f.y;
+        acc[1] += r.x * r.x + r.y * r.y;
+    }
+    if (grid_reduce<2>(acc, partials, ticket)) {
+        if (threadIdx.x == 0) {
+            sums_out[0] = acc[0];
+            sums_out[1] = acc[1];
+        }
+    }
+}
+
+// x += e (double += single)
+__global__ void __launch_bounds__(kBlock) k_mixed_correct(cplx* __restrict__ x, const cplxf* __restrict__ e32, int n_elems) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += stride) {
+        const cplxf e = ld_stream(e32 + i);
+        cplx v = x[i];
+        v.x += (double)e.x;
+        v.y += (double)e.y;
+        x[i] = v;
+    }
+}
+
+// inner solve starts from e = 0: r_in = r_outer, |r_in|^2 known; stop at |r_in| < delta |r_outer|
+__global__ void k_mixed_begin(CgState* st, const double* sums /* |phi|^2, |r|^2 */, double delta) {
+    st->done = 0;
+    st->iters = 0;
+    st->converged = 0;
+    st->pending = 0;
+    st->pending_buf = 0;
+    st->k = 0;
+    st->phi_norm2 = sums[1];
+    st->rr[0] = sums[1];
+    st->tol = delta;
 }
 
 __global__ void k_cg_clear_pending(CgState* st) { st->pending = 0; }

@@ -60,6 +60,8 @@ struct CgState {
     int pending;        // fused path: an x update is owed
     int pending_buf;    // ... with d in ping-pong buffer 0/1
     int k;              // iteration counter kept on the device (one-pass path: kernels are replayed from a CUDA graph)
+    int pad;
+    double tol;         // one-pass path: relative tolerance of the running solve (kept here so graphs do not bake it)
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -357,10 +359,10 @@ __global__ void k_cg_check(CgState* st, int k, double tol, int max_iter) {
 }
 
 // the same with the device-side iteration counter (one-pass path)
-__global__ void k_cg_check_dev(CgState* st, double tol, int max_iter) {
+__global__ void k_cg_check_dev(CgState* st, int max_iter) {
     if (st->done) return;
     const int k = st->k;
-    if (cg_converged(st, k & 1, tol)) {
+    if (cg_converged(st, k & 1, st->tol)) {
         st->iters = k - 1;
         st->converged = 1;
         st->done = 1;
@@ -371,7 +373,8 @@ __global__ void k_cg_check_dev(CgState* st, double tol, int max_iter) {
     }
 }
 
-__global__ void k_cg_reset(CgState* st) {
+__global__ void k_cg_reset(CgState* st, double tol) {
+    st->tol = tol;
     st->done = 0;
     st->iters = 0;
     st->converged = 0;

@@ -135,6 +135,10 @@ class Lattice:
         check(self.lib.sm_set_cg(self.ctx, float(tol), int(max_iter)))
         self.tol, self.max_iter = float(tol), int(max_iter)
 
+    def set_solver(self, mixed_precision: bool):
+        """False: the reference's double-precision CG (default).  True: opt-in mixed-precision defect correction."""
+        check(self.lib.sm_set_solver(self.ctx, _abi.SM_SOLVER_MIXED if mixed_precision else _abi.SM_SOLVER_REFERENCE))
+
     def last_kernel_ms(self) -> float:
         ms = C.c_double()
         check(self.lib.sm_last_kernel_ms(self.ctx, C.byref(ms)))

@@ -440,3 +440,34 @@ def test_config5_near_critical_cg_vs_oracle(sb):
     assert res <= 5e-10
     assert relerr(x, xo) <= 1e-7
     lat.close()
+
+
+def test_mixed_precision_solver_opt_in(sb):
+    """single-precision inner CG inside a double-precision defect correction.  Same stopping rule on the
+    TRUE residual; the iterate differs from the reference's, so the bar is the residual and a loose solution match."""
+    from oracle.port import gaussian_fields
+    for n, m0 in [(384, 0.0), (512, -0.05)]:
+        rng = np.random.default_rng(n)
+        U = np.exp(2j * np.pi * rng.random((2, n * n)))
+        phi, _ = gaussian_fields(n, n, 3)
+        lat = sb.Lattice(n, n)
+        x64, ok64, its64 = lat.conjugate_gradient(U, phi, m0)
+        lat.set_solver(True)
+        x32, ok32, its32 = lat.conjugate_gradient(U, phi, m0)
+        assert ok64 == ok32 == 1
+        res = np.linalg.norm(phi - lat.D_D_dagger_phi(U, x32, m0)) / np.linalg.norm(phi)
+        assert res < 1e-10                                   # the reference's criterion, on the true residual
+        assert relerr(x32, x64) <= 1e-7
+        assert its32 <= 2 * its64 + 20
+        # a trajectory with the opt-in solver: dH agrees with the reference solver far below Metropolis relevance
+        chi, pi = gaussian_fields(n, n, 4)
+        out = []
+        for mixed in (False, True):
+            lat.set_solver(mixed)
+            lat.hmc_configure(2.0, m0, 4, 0.2)
+            lat.hmc_set_gauge(U)
+            lat.hmc_inject(pi, chi)
+            out.append(lat.hmc_trajectory())
+        assert out[1].cg_all_converged == 1
+        assert abs(out[0].dH - out[1].dH) <= 1e-5 * max(1.0, abs(out[0].H_old) * 1e-3)
+        lat.close()

@@ -20,9 +20,12 @@ for n in sizes:
         env = dict(p.split("=") for p in path.split(":")[1:])
         os.environ["SM_DD_PATH"] = path.split(":")[0]
         os.environ.update(env)
+        mixed = env.pop("MIXED", None)
         lat = sb.Lattice(n, n)
         for k in ["SM_DD_PATH", *env]:
             os.environ.pop(k)
+        if mixed:
+            lat.set_solver(True)
         dU, dphi, dout, dx = lat.new_field(True, U), lat.new_field(True, phi), lat.new_field(), lat.new_field()
         reps = max(3, min(200, int(2e9 / V / 20)))
         lat.dev_DDdag_loop(dU, dphi, dout, 0.0, 3)
