@@ -519,7 +519,7 @@ static int launch_fused(sm_ctx* c, const C* U, const C* in, C* out, double m0, d
     a.chunk_mode = 0;
     // rows in flight per block: as many as 2 blocks per SM leave shared memory for (single precision moves
     // half the bytes per row, so it keeps more rows in flight)
-    constexpr int STAGES = kDouble ? ((MODE == FUSED_CG) ? 2 : 3) : 4;
+    constexpr int STAGES = kDouble ? ((MODE == FUSED_CG) ? 2 : 3) : 3;
     const size_t smem = fused_smem_bytes(MODE, STAGES, c->fus_block.x, sizeof(C));
     const unsigned int attr_bit = 1u << (MODE + (kDouble ? 0 : 4));
     if (!(c->attr_done & attr_bit)) {   // function attributes are per device: once per context and instantiation

@@ -111,6 +111,7 @@ constexpr size_t fused_smem_bytes(int mode, int stages, int BT, size_t elem_byte
 template <typename C, int MODE, int STAGES>
 __global__ void __launch_bounds__(kBlock, 2) k_dd_fused(const FusedArgsT<C> a) {
     typedef typename RealOf<C>::type R;
+    static_assert(6 % STAGES == 0, "the stage ring is indexed with the unrolled step: STAGES must divide 6");
     extern __shared__ __align__(16) unsigned char s_raw[];
     C* const s_mem = reinterpret_cast<C*>(s_raw);
     constexpr int NARR = fused_arrays(MODE);
