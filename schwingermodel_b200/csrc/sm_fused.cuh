@@ -3,20 +3,26 @@
 // The two-pass form (k_wilson twice) moves 192 B per site-update because the intermediate
 // t = D^dagger psi goes out to HBM and comes back.  Here a block owns a strip of columns
 // (t direction) and marches down the x rows keeping, per thread (= per column),
-//     psi rows j-2, j-1, j      t rows j-3, j-2, j-1      and the links of those rows
-// in REGISTERS; the t-direction neighbours travel through a small double-buffered shared-memory
-// line of pre-projected half-spinors (the same rank-1 trick the halo exchange uses), one
-// __syncthreads per row.  Rows are staged from HBM into a shared-memory ring with cp.async
-// (16 B per thread and array, L1 bypassed, STAGES-1 rows in flight per block) so the loads never
-// occupy registers or stall the step.  Each step takes row j, forms t(j-1) = D^dagger psi and
-// out(j-2) = D t, so psi and U are read once and out is written once: ~96 B per site-update
-// plus the halo overhead (2 columns each side of a (BT-4)-wide strip, 4 rows per chunk).
+//     psi rows j, j-1, j-2      t rows j-1, j-2      the finished -x hop term of t row j-3
+//     and the links of rows j, j-1, j-2
+// in REGISTERS, as rings whose slots are compile-time constants after a 6-fold unroll of the row
+// loop (rotating the window costs no instruction).  The t-direction neighbours travel through a
+// small double-buffered shared-memory line of pre-projected half-spinors (the same rank-1 trick
+// the halo exchange uses), one __syncthreads per row.  Rows are staged from HBM into a
+// shared-memory ring with cp.async (16 B per thread and array, L1 bypassed, STAGES-1 rows in
+// flight per block) so the loads never occupy registers or stall the step.  Each step takes row
+// j, forms t(j-1) = D^dagger psi and out(j-2) = D t, so psi and U are read once and out is
+// written once: ~96 B per site-update plus the halo overhead (2 columns each side of a strip,
+// 4 rows per chunk).
 //
 // FUSED_CG additionally folds the CG vector updates that touch the same data into the pass
 // (src/conjugate_gradient.cpp:32-59):  d_k = r_k + beta d_{k-1} is formed on load (also at the
 // halo sites, from r and d_{k-1}), x += alpha_{k-1} d_{k-1} is applied where d_{k-1} is read, and
 // dot(d_k, A d_k) is reduced in the epilogue.  With k_cg_resid (r -= alpha A d, |r|^2) one CG
 // iteration moves 224 + 96 = 320 B per site instead of 512.
+//
+// Everything is templated on the complex type: cplx (double2) is the reference-exact path, cplxf
+// (float2) the inner solve of the opt-in mixed-precision CG.
 #pragma once
 #include "sm_kernels.cuh"
 
@@ -47,7 +53,6 @@ struct FusedArgsT {
     C* d_new;         // d_k
     int first;           // iteration 0: d_0 = r_0, no x update owed
     int cur;             // parity of the iteration (selects rr[], the d ping-pong is in the pointers)
-    double tol;
     // lattice split along x (ranks_t == 1): rows -2,-1 ("lo") and wx, wx+1 ("hi") live in ghost
     // arrays laid out [component][2 rows][wt]; null = wrap inside the tile
     const C* gU_lo;
@@ -431,8 +436,6 @@ __global__ void k_mixed_begin(CgState* st, const double* sums /* |phi|^2, |r|^2 
     st->rr[0] = sums[1];
     st->tol = delta;
 }
-
-__global__ void k_cg_clear_pending(CgState* st) { st->pending = 0; }
 
 // ----------------------------------------------------------------------------------------------
 // Halo push over NVLink peer memory (lattice split along x).  Instead of a send/recv pair, the
