@@ -1,0 +1,338 @@
+// sm_cg.cuh -- conjugate-gradient drivers: two-pass, one-pass (+ CUDA graphs), mixed precision, cluster / grid resident.
+// Part of the single translation unit sm_abi.cu (static functions, included in dependency order).
+#pragma once
+#include "sm_ops.cuh"
+
+// conjugate_gradient (src/conjugate_gradient.cpp:4-67) entirely on the device.  The host only
+// enqueues batches of iterations and polls a pinned copy of the CG scalars one batch behind, so
+// the GPU never waits for it; once the stopping rule has fired every later kernel of the queue
+// returns at its first instruction.
+static int dev_cg_twopass(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, int* converged, int* iterations) {
+    TRY(ensure_complex(c, &c->tmp));
+    TRY(ensure_complex(c, &c->cg_r));
+    TRY(ensure_complex(c, &c->cg_d));
+    TRY(ensure_complex(c, &c->cg_Ad));
+    const int n_elems = 2 * c->V;
+    const double tol = c->tol;
+    const int max_iter = c->max_iter;
+    CgState* st = c->cg;
+    const int* done = &st->done;
+
+    k_cg_reset<<<1, 1, 0, c->stream>>>(st, tol);
+    c->launches++;
+    // Ad = DD^dagger phi ; r = phi - Ad ; d = r ; x = phi ; |phi|^2, |r|^2
+    TRY((launch_wilson<true, WILSON_PLAIN>(c, U, phi, c->tmp, m0)));
+    TRY((launch_wilson<false, WILSON_CGINIT>(c, U, c->tmp, nullptr, m0, phi, c->cg_r, c->cg_d, x,
+                                             sum_target(c, &st->phi_norm2))));
+    TRY(sum_finish(c, &st->phi_norm2, 2));
+
+    const int batch = 8;
+    int k = 0, slot = 0, prev = -1;
+    for (;;) {
+        const int k_end = std::min(max_iter, k + batch);
+        for (; k < k_end; k++) {
+            const int cur = k & 1;
+            if (k > 0) {
+                k_cg_dir<<<c->flat_blocks_c, kBlock, 0, c->stream>>>(st, k, tol, c->cg_r, c->cg_d, n_elems);
+                KCHECK();
+                c->launches++;
+            }
+            TRY((launch_wilson<true, WILSON_PLAIN>(c, U, c->cg_d, c->tmp, m0, nullptr, nullptr, nullptr, nullptr,
+                                                   nullptr, done)));
+            TRY((launch_wilson<false, WILSON_DOT>(c, U, c->tmp, c->cg_Ad, m0, c->cg_d, nullptr, nullptr, nullptr,
+                                                  sum_target(c, st->dAd), done)));
+            TRY(sum_finish(c, st->dAd, 2));
+            k_cg_update<<<c->flat_blocks_c, kBlock, 0, c->stream>>>(st, cur, x, c->cg_d, c->cg_r, c->cg_Ad, n_elems,
+                                                                    c->partials, c->tickets + TK_UPDATE,
+                                                                    sum_target(c, &st->rr[cur ^ 1]));
+            KCHECK();
+            c->launches++;
+            TRY(sum_finish(c, &st->rr[cur ^ 1], 1));
+        }
+        // stopping rule of the batch's last iteration; at k == max_iter this always sets `done`
+        k_cg_check<<<1, 1, 0, c->stream>>>(st, k, tol, max_iter);
+        KCHECK();
+        c->launches++;
+        CU(cudaMemcpyAsync(&c->h->cg[slot], st, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaEventRecord(c->ev_poll[slot], c->stream));
+        // look one batch behind so the queue never drains while the host waits
+        if (prev >= 0) {
+            CU(cudaEventSynchronize(c->ev_poll[prev]));
+            if (c->h->cg[prev].done) break;
+        }
+        if (k >= max_iter) break;
+        prev = slot;
+        slot ^= 1;
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpyAsync(&c->h->cg[0], st, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (converged) *converged = c->h->cg[0].converged;
+    if (iterations) *iterations = c->h->cg[0].iters;
+    return SM_OK;
+}
+
+// The same algorithm on the one-pass D D^dagger: per iteration k
+//   A(k): stopping rule of k-1 ; d_k = r_k + beta d_{k-1} ; x += alpha_{k-1} d_{k-1} ; Ad = D D^dagger d_k ; dot(d_k, Ad)
+//   B(k): alpha_k = r_norm2 / dot ; r -= alpha_k Ad ; |r|^2
+// and one k_cg_flush_x at the end for the x update the loop still owes.  320 B per site and iteration
+// (160 B in single precision).  On entry CgState holds |r|^2 in rr[0], the reference norm in phi_norm2, the
+// tolerance, k = 0; r holds the residual of the start vector x.
+template <typename C>
+static int cg_fused_loop(sm_ctx* c, const C* U, C* r, C* x, C* dbuf0, C* dbuf1, C* Ad, double m0, int max_iter) {
+    const int n_elems = 2 * c->V;
+    CgState* st = c->cg;
+    C* dbuf[2] = {dbuf0, dbuf1};
+
+    // one iteration: A(k) then B(k) (+ the all-reduces of their sums on a split lattice)
+    auto iteration = [&](int k) -> int {
+        const int cur = k & 1;
+        TRY((launch_fused<C, FUSED_CG>(c, U, dbuf[cur ^ 1], Ad, m0, sum_target(c, st->dAd), r, x, dbuf[cur], k)));
+        TRY(sum_finish(c, st->dAd, 2));
+        k_cg_resid<C><<<c->flat_blocks_c, kBlock, 0, c->stream>>>(st, cur, r, Ad, n_elems, c->partials,
+                                                                  c->tickets + TK_UPDATE, sum_target(c, &st->rr[cur ^ 1]));
+        KCHECK();
+        c->launches++;
+        return sum_finish(c, &st->rr[cur ^ 1], 1);
+    };
+    const int batch = 8;   // even: a replayed batch always starts on the same parity
+
+    // a batch of iterations k = 1 + 8 m ... as one CUDA graph (single tile; the iteration index and the
+    // tolerance live in CgState, so the nodes are iteration- and tolerance-independent)
+    cudaGraphExec_t exec = nullptr;
+    int graph_kernels = 0;
+    const bool graphs = c->use_graphs && !c->dist() && max_iter > batch;
+    if (graphs) {
+        for (auto& g : c->cg_graphs)
+            if (g.U == (const void*)U && g.x == (const void*)x && g.m0 == m0 && g.max_iter == max_iter) {
+                exec = g.exec;
+                graph_kernels = g.kernels;
+            }
+    }
+
+    int k = 0, slot = 0, prev = -1;
+    TRY(iteration(k++));   // k = 0 is special (d_0 = r_0) and also sets the kernel attributes before any capture
+    if (graphs && exec == nullptr) {
+        const long long l0 = c->launches;
+        cudaGraph_t graph = nullptr;
+        CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = SM_OK;
+        for (int i = 0; i < batch && rc == SM_OK; i++) rc = iteration(1 + i);
+        if (rc == SM_OK) {
+            k_cg_check_dev<<<1, 1, 0, c->stream>>>(st, max_iter);
+            c->launches++;
+        }
+        cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+        if (rc != SM_OK) return rc;
+        if (e != cudaSuccess) return fail(SM_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+        graph_kernels = (int)(c->launches - l0);
+        c->launches = l0;
+        CU(cudaGraphInstantiate(&exec, graph, 0));
+        cudaGraphDestroy(graph);
+        if (c->cg_graphs.size() >= 16) {
+            cudaGraphExecDestroy(c->cg_graphs.front().exec);
+            c->cg_graphs.erase(c->cg_graphs.begin());
+        }
+        c->cg_graphs.push_back({(const void*)U, (const void*)x, m0, max_iter, exec, graph_kernels});
+    }
+    for (;;) {
+        if (exec != nullptr && k + batch <= max_iter) {
+            CU(cudaGraphLaunch(exec, c->stream));
+            c->launches += graph_kernels;
+            k += batch;
+        } else {
+            const int k_end = std::min(max_iter, k + batch);
+            for (; k < k_end; k++) TRY(iteration(k));
+            k_cg_check_dev<<<1, 1, 0, c->stream>>>(st, max_iter);
+            KCHECK();
+            c->launches++;
+        }
+        CU(cudaMemcpyAsync(&c->h->cg[slot], st, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaEventRecord(c->ev_poll[slot], c->stream));
+        if (prev >= 0) {
+            CU(cudaEventSynchronize(c->ev_poll[prev]));
+            if (c->h->cg[prev].done) break;
+        }
+        if (k >= max_iter) break;
+        prev = slot;
+        slot ^= 1;
+    }
+    k_cg_flush_x<C><<<c->flat_blocks_c, kBlock, 0, c->stream>>>(st, x, dbuf[0], dbuf[1], n_elems);
+    KCHECK();
+    c->launches++;
+    CU(cudaMemcpyAsync(&c->h->cg[0], st, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return SM_OK;
+}
+
+// the reference's algorithm, double precision throughout
+static int dev_cg_fused(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, int* converged, int* iterations) {
+    TRY(ensure_complex(c, &c->tmp));
+    TRY(ensure_complex(c, &c->cg_r));
+    TRY(ensure_complex(c, &c->cg_d));
+    TRY(ensure_complex(c, &c->cg_d2));
+    TRY(ensure_complex(c, &c->cg_Ad));
+    CgState* st = c->cg;
+    k_cg_reset<<<1, 1, 0, c->stream>>>(st, c->tol);
+    c->launches++;
+    // x = phi ; r = phi - D D^dagger phi ; |phi|^2, |r|^2   (d_0 = r_0 is formed by the first pass)
+    TRY((launch_wilson<true, WILSON_PLAIN>(c, U, phi, c->tmp, m0)));
+    TRY((launch_wilson<false, WILSON_CGINIT>(c, U, c->tmp, nullptr, m0, phi, c->cg_r, c->cg_d2, x,
+                                             sum_target(c, &st->phi_norm2))));
+    TRY(sum_finish(c, &st->phi_norm2, 2));
+    TRY(cg_fused_loop<cplx>(c, U, c->cg_r, x, c->cg_d, c->cg_d2, c->cg_Ad, m0, c->max_iter));
+    if (converged) *converged = c->h->cg[0].converged;
+    if (iterations) *iterations = c->h->cg[0].iters;
+    return SM_OK;
+}
+
+// Opt-in (sm_set_solver(SM_SOLVER_MIXED)): defect correction in double precision around an inner CG in
+// single precision.  x = phi; repeat { r = phi - A x (double, true residual); stop if |r| < tol |phi|;
+// solve A e = r in single precision to a relative delta; x += e }.  Half the bytes per inner iteration.
+// The result meets the same residual criterion (checked on the TRUE residual) but is a different iterate
+// than the reference's, so dH parity at 1e-8 does not hold: SURVEY 8(f).4 "solver upgrades".
+static int dev_cg_mixed(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, int* converged, int* iterations) {
+    TRY(ensure_complex(c, &c->cg_Ad));
+    const size_t n2 = 2 * (size_t)c->V;
+    if (!c->mx_U) {
+        TRY(dev_alloc(&c->mx_U, n2));
+        TRY(dev_alloc(&c->mx_r, n2));
+        TRY(dev_alloc(&c->mx_e, n2));
+        TRY(dev_alloc(&c->mx_d0, n2));
+        TRY(dev_alloc(&c->mx_d1, n2));
+        TRY(dev_alloc(&c->mx_Ad, n2));
+        CU(cudaMemsetAsync(c->mx_d0, 0, sizeof(cplxf) * n2, c->stream));
+        CU(cudaMemsetAsync(c->mx_d1, 0, sizeof(cplxf) * n2, c->stream));
+    }
+    const int n_elems = (int)n2;
+    k_to_single<<<c->flat_blocks_c, kBlock, 0, c->stream>>>(U, c->mx_U, n_elems);
+    KCHECK();
+    c->launches++;
+    CU(cudaMemcpyAsync(x, phi, sizeof(cplx) * n2, cudaMemcpyDeviceToDevice, c->stream));   // x0 = phi as the reference
+    int total = 0, ok = 0;
+    const int max_cycles = 12;
+    for (int cycle = 0; cycle < max_cycles; cycle++) {
+        TRY((launch_fused<cplx, FUSED_PLAIN>(c, U, x, c->cg_Ad, m0)));
+        k_mixed_residual<<<c->flat_blocks_c, kBlock, 0, c->stream>>>(phi, c->cg_Ad, c->mx_r, c->mx_e, n_elems, c->partials,
+                                                                     c->tickets + TK_DOT, c->sums + 12);
+        KCHECK();
+        c->launches++;
+        CU(cudaMemcpyAsync(c->h->sums + 12, c->sums + 12, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        const double pp = c->h->sums[12], rr = c->h->sums[13];
+        if (std::sqrt(rr) < c->tol * std::sqrt(pp)) {
+            ok = 1;
+            break;
+        }
+        if (total >= c->max_iter || cycle == max_cycles - 1) break;
+        // do not over-solve the last cycle; single precision stalls near 1e-6
+        const double need = 0.5 * c->tol * std::sqrt(pp) / std::sqrt(rr);
+        const double delta = std::min(0.1, std::max(1e-5, need));
+        k_mixed_begin<<<1, 1, 0, c->stream>>>(c->cg, c->sums + 12, delta);
+        KCHECK();
+        c->launches++;
+        TRY(cg_fused_loop<cplxf>(c, c->mx_U, c->mx_r, c->mx_e, c->mx_d0, c->mx_d1, c->mx_Ad, m0,
+                                 std::max(1, c->max_iter - total)));
+        total += c->h->cg[0].converged ? c->h->cg[0].iters + 1 : c->h->cg[0].iters;
+        k_mixed_correct<<<c->flat_blocks_c, kBlock, 0, c->stream>>>(x, c->mx_e, n_elems);
+        KCHECK();
+        c->launches++;
+    }
+    if (converged) *converged = ok;
+    if (iterations) *iterations = total;
+    return SM_OK;
+}
+
+// small lattices: the whole solve in one launch, every site resident in one thread (sm_cluster_cg.cuh):
+// one thread-block cluster up to 4096 sites, a cooperative grid up to one 512-thread CTA per SM
+static int resident_args(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, ResidentCgArgs* a) {
+    *a = ResidentCgArgs{};
+    a->U = U;
+    a->phi = phi;
+    a->x = x;
+    a->wx = c->wx;
+    a->wt = c->wt;
+    a->V = c->V;
+    a->mass = m0 + 2;
+    a->sR_edge = c->sR_edge();
+    a->sL_edge = c->sL_edge();
+    a->tol = c->tol;
+    a->max_iter = c->max_iter;
+    a->st = c->cg;
+    return SM_OK;
+}
+
+static int resident_finish(sm_ctx* c, int* converged, int* iterations) {
+    c->launches++;
+    CU(cudaMemcpyAsync(&c->h->cg[0], c->cg, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (converged) *converged = c->h->cg[0].converged;
+    if (iterations) *iterations = c->h->cg[0].iters;
+    return SM_OK;
+}
+
+static int dev_cg_cluster(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, int* converged, int* iterations) {
+    ResidentCgArgs a;
+    TRY(resident_args(c, U, phi, x, m0, &a));
+    int ctas = 1;
+    while (ctas * kClusterThreads < c->V) ctas *= 2;
+    if (!(c->attr_done & (1u << 8))) {
+        CU(cudaFuncSetAttribute(k_cg_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        c->attr_done |= 1u << 8;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas, 1, 1);
+    cfg.blockDim = dim3(kClusterThreads, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = ctas;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CU(cudaLaunchKernelEx(&cfg, k_cg_cluster, a));
+    return resident_finish(c, converged, iterations);
+}
+
+// how many sites the cooperative-grid solve can hold on this device (0: not available)
+static int coop_capacity(sm_ctx* c) {
+    if (c->coop_sites < 0) {
+        int per_sm = 0, coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
+        if (!coop || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_coop, kCoopThreads, 0) != cudaSuccess)
+            per_sm = 0;
+        c->coop_sites = per_sm * c->sm_count * kCoopThreads;
+    }
+    return c->coop_sites;
+}
+
+static int dev_cg_coop(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, int* converged, int* iterations) {
+    ResidentCgArgs a;
+    TRY(resident_args(c, U, phi, x, m0, &a));
+    const int blocks = (c->V + kCoopThreads - 1) / kCoopThreads;
+    if (!c->coop_hop) {
+        TRY(dev_alloc(&c->coop_hop, (size_t)8 * c->V));
+        TRY(dev_alloc(&c->coop_wsum, (size_t)4 * blocks * (kCoopThreads / 32)));
+        TRY(dev_alloc(&c->coop_bar, (size_t)32));
+    }
+    CU(cudaMemsetAsync(c->coop_bar, 0, sizeof(unsigned int) * 32, c->stream));
+    a.hop = c->coop_hop;
+    a.wsum = c->coop_wsum;
+    a.bar = c->coop_bar;
+    void* params[] = {&a};
+    CU(cudaLaunchCooperativeKernel((const void*)k_cg_coop, dim3(blocks, 1, 1), dim3(kCoopThreads, 1, 1), params, 0,
+                                   c->stream));
+    return resident_finish(c, converged, iterations);
+}
+
+static int dev_cg(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, int* converged, int* iterations) {
+    if (c->use_cluster && !c->dist()) {
+        if (c->V <= kClusterMaxCtas * kClusterThreads) return dev_cg_cluster(c, U, phi, x, m0, converged, iterations);
+        if (c->V <= coop_capacity(c)) return dev_cg_coop(c, U, phi, x, m0, converged, iterations);
+    }
+    if (c->solver == SM_SOLVER_MIXED && fused_ok(c) && !c->dist()) return dev_cg_mixed(c, U, phi, x, m0, converged, iterations);
+    if (fused_ok(c)) return dev_cg_fused(c, U, phi, x, m0, converged, iterations);
+    return dev_cg_twopass(c, U, phi, x, m0, converged, iterations);
+}

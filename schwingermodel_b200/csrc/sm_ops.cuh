@@ -1,0 +1,226 @@
+// sm_ops.cuh -- operator launches on device fields: Wilson stencil, one-pass D D^dagger (+ 2-row ghosts, peer-memory halos), dot.
+// Part of the single translation unit sm_abi.cu (static functions, included in dependency order).
+#pragma once
+#include "sm_dist.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// operator launches on device fields
+// ------------------------------------------------------------------------------------------------
+template <bool DAG, int MODE>
+static int launch_wilson(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, double m0, const cplx* aux = nullptr,
+                         cplx* r = nullptr, cplx* d = nullptr, cplx* x = nullptr, double* sums_out = nullptr,
+                         const int* done = nullptr) {
+    if (c->dist()) TRY((exchange_spinor_halo<DAG>(c, U, in, done)));
+    WilsonArgs a{};
+    a.U = U;
+    a.in = in;
+    a.out = out;
+    a.aux = aux;
+    a.r = r;
+    a.d = d;
+    a.x = x;
+    a.wx = c->wx;
+    a.wt = c->wt;
+    a.V = c->V;
+    a.rows_per_block = c->rows_per_block;
+    a.mass = m0 + 2;
+    a.sR_edge = c->sR_edge();
+    a.sL_edge = c->sL_edge();
+    a.g_tp = c->rt > 1 ? c->g_tp : nullptr;
+    a.g_tm = c->rt > 1 ? c->g_tm : nullptr;
+    a.g_xp = c->rx > 1 ? c->g_xp : nullptr;
+    a.g_xm = c->rx > 1 ? c->g_xm : nullptr;
+    a.partials = c->partials;
+    a.ticket = c->tickets + TK_WILSON;
+    a.sums_out = sums_out;
+    a.done = done;
+    k_wilson<DAG, MODE><<<c->wil_grid, c->wil_block, 0, c->stream>>>(a);
+    KCHECK();
+    c->launches++;
+    return SM_OK;
+}
+
+static int dev_D(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, double m0, bool dagger) {
+    if (in == out) return fail(SM_ERR_ARG, "D: in and out must not alias");
+    if (dagger) return launch_wilson<true, WILSON_PLAIN>(c, U, in, out, m0);
+    return launch_wilson<false, WILSON_PLAIN>(c, U, in, out, m0);
+}
+
+// D D^dagger via the context's scratch field (the reference's global DTEMP, dirac_operator.cpp:477-480)
+// ---- peer-memory window ------------------------------------------------------------------------
+static size_t win_ghost_elems(const sm_ctx* c) { return 4 * (size_t)c->wt; }
+static cplx* win_ghost(const sm_ctx* c, void* base, int kind, int parity, int side) {
+    return (cplx*)base + (size_t)((kind * 2 + parity) * 2 + side) * win_ghost_elems(c);
+}
+static unsigned int* win_flag(const sm_ctx* c, void* base, int kind, int side) {
+    return (unsigned int*)((char*)base + sizeof(cplx) * 8 * win_ghost_elems(c)) + kind * 2 + side;
+}
+
+// push my boundary rows of `field` into both neighbours' ghosts (epoch parity) and raise their flags
+static int p2p_push(sm_ctx* c, const cplx* field, int kind, cudaStream_t st) {
+    const unsigned int epoch = ++c->p2p_epoch[kind];
+    const int parity = epoch & 1;
+    const int n = 8 * c->wt;
+    const int blocks = std::max(1, std::min(64, (n + kBlock - 1) / kBlock));
+    k_push_rows<<<blocks, kBlock, 0, st>>>(field, c->wx, c->wt, c->V, win_ghost(c, c->peer_win[0], kind, parity, 1),
+                                           win_ghost(c, c->peer_win[1], kind, parity, 0),
+                                           win_flag(c, c->peer_win[0], kind, 1), win_flag(c, c->peer_win[1], kind, 0),
+                                           epoch, c->push_ticket);
+    KCHECK();
+    c->launches++;
+    return SM_OK;
+}
+
+// make `st` wait until both neighbours have delivered the current epoch of `kind`
+static int p2p_wait(sm_ctx* c, int kind, cudaStream_t st) {
+    const unsigned int epoch = c->p2p_epoch[kind];
+    for (int side = 0; side < 2; side++) {
+        CUresult r = c->wait_value32((CUstream)st, (CUdeviceptr)win_flag(c, c->win, kind, side), epoch,
+                                     CU_STREAM_WAIT_VALUE_GEQ);
+        if (r != CUDA_SUCCESS) return fail(SM_ERR_CUDA, "cuStreamWaitValue32 failed (" + std::to_string((int)r) + ")");
+    }
+    return SM_OK;
+}
+
+// two boundary rows of a field (rows 0,1 to the -x neighbour, rows wx-2,wx-1 to the +x neighbour) into
+// the [comp][2][wt] ghost arrays; rows are contiguous in HBM, so nothing is packed
+static int exchange_rows2(sm_ctx* c, const cplx* field, cplx* lo_dst, cplx* hi_dst, cudaStream_t st = nullptr) {
+    if (st == nullptr) st = c->stream;
+    const size_t n = 2 * (size_t)c->wt;   // complex per component
+    NC(g_nccl.GroupStart());
+    for (int comp = 0; comp < 2; comp++) {
+        const cplx* f = field + (size_t)comp * c->V;
+        NC(g_nccl.Send(f, 2 * n, ncclDouble, c->nb_xm, c->comm, st));
+        NC(g_nccl.Send(f + (size_t)(c->wx - 2) * c->wt, 2 * n, ncclDouble, c->nb_xp, c->comm, st));
+        NC(g_nccl.Recv(hi_dst + comp * n, 2 * n, ncclDouble, c->nb_xp, c->comm, st));
+        NC(g_nccl.Recv(lo_dst + comp * n, 2 * n, ncclDouble, c->nb_xm, c->comm, st));
+    }
+    NC(g_nccl.GroupEnd());
+    return SM_OK;
+}
+
+// one-pass D D^dagger (sm_fused.cuh): a single tile, or tiles split along x only (ranks_t == 1,
+// 2-row ghosts); a split along t keeps the two-pass kernels.  C = cplx (double) everywhere except in the
+// inner solve of the opt-in mixed-precision CG (C = cplxf, single tile only).
+template <typename C, int MODE>
+static int launch_fused(sm_ctx* c, const C* U, const C* in, C* out, double m0, double* sums_out = nullptr,
+                        const C* r = nullptr, C* x = nullptr, C* d_new = nullptr, int k = 0) {
+    constexpr bool kDouble = std::is_same<C, cplx>::value;
+    if (!kDouble && c->dist()) return fail(SM_ERR_STATE, "single-precision passes run on a single tile only");
+    FusedArgsT<C> a{};
+    a.U = U;
+    a.in = in;
+    a.out = out;
+    a.wx = c->wx;
+    a.wt = c->wt;
+    a.V = c->V;
+    a.rows_per_block = c->fus_rows;
+    a.cols_per_strip = c->fus_cols;
+    a.mass = m0 + 2;
+    a.sR_edge = c->sR_edge();
+    a.sL_edge = c->sL_edge();
+    a.partials = c->partials;
+    a.ticket = c->tickets + TK_WILSON;
+    a.sums_out = sums_out;
+    a.st = c->cg;
+    a.r = r;
+    a.x = x;
+    a.d_new = d_new;
+    a.first = (k == 0);
+    a.cur = k & 1;
+    a.nchunks = c->fus_grid.y;
+    a.chunk_mode = 0;
+    // rows in flight per block: as many as 2 blocks per SM leave shared memory for (single precision moves
+    // half the bytes per row, so it keeps more rows in flight)
+    constexpr int STAGES = kDouble ? ((MODE == FUSED_CG) ? 2 : 3) : 3;
+    const size_t smem = fused_smem_bytes(MODE, STAGES, c->fus_block.x, sizeof(C));
+    const unsigned int attr_bit = 1u << (MODE + (kDouble ? 0 : 4));
+    if (!(c->attr_done & attr_bit)) {   // function attributes are per device: once per context and instantiation
+        CU(cudaFuncSetAttribute(k_dd_fused<C, MODE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        c->attr_done |= attr_bit;
+    }
+    bool split_launch = false;
+    if constexpr (kDouble) {
+        if (c->dist()) {
+            if (c->f2_U_valid_for != U) {
+                TRY(exchange_rows2(c, U, c->f2_U[0], c->f2_U[1]));
+                c->f2_U_valid_for = U;
+            }
+            a.gU_lo = c->f2_U[0];
+            a.gU_hi = c->f2_U[1];
+            // the ghost rows this pass needs: psi (PLAIN) or r (CG; d_{k-1} ghosts were written by the previous
+            // pass).  Only the two boundary bands read them, so the exchange runs on the comm stream while the
+            // interior chunks compute.
+            const cplx* moving = (MODE == FUSED_CG) ? r : in;
+            const int kind = (MODE == FUSED_CG) ? 1 : 0;
+            cplx* dst[2] = {(MODE == FUSED_CG) ? c->f2_r[0] : c->f2_in[0], (MODE == FUSED_CG) ? c->f2_r[1] : c->f2_in[1]};
+            split_launch = c->overlap && c->fus_split_chunks >= 1;
+            cudaStream_t xs = split_launch ? c->comm_stream : c->stream;
+            if (c->p2p) TRY(p2p_push(c, moving, kind, c->stream));   // stores into the neighbours' windows
+            if (split_launch) {
+                CU(cudaEventRecord(c->ev_ready, c->stream));
+                CU(cudaStreamWaitEvent(c->comm_stream, c->ev_ready, 0));
+            }
+            if (c->p2p) {
+                TRY(p2p_wait(c, kind, xs));                           // ... and waits for theirs in mine
+                const int parity = c->p2p_epoch[kind] & 1;
+                dst[0] = win_ghost(c, c->win, kind, parity, 0);
+                dst[1] = win_ghost(c, c->win, kind, parity, 1);
+            } else {
+                TRY(exchange_rows2(c, moving, dst[0], dst[1], xs));
+            }
+            if (MODE == FUSED_CG) {
+                const int cur = k & 1;
+                a.gin_lo = c->f2_d[cur ^ 1][0];
+                a.gin_hi = c->f2_d[cur ^ 1][1];
+                a.gd_lo = c->f2_d[cur][0];
+                a.gd_hi = c->f2_d[cur][1];
+                a.gr_lo = dst[0];
+                a.gr_hi = dst[1];
+            } else {
+                a.gin_lo = dst[0];
+                a.gin_hi = dst[1];
+            }
+        }
+    }
+    if (split_launch) {
+        // boundary bands follow the exchange on the comm stream; the interior runs meanwhile
+        a.rb = c->fus_rb;
+        a.rows_per_block = c->fus_split_rows;
+        a.nchunks = c->fus_split_chunks + 2;
+        a.chunk_mode = 2;
+        k_dd_fused<C, MODE, STAGES><<<dim3(c->fus_grid.x, 2, 1), c->fus_block, smem, c->comm_stream>>>(a);
+        KCHECK();
+        CU(cudaEventRecord(c->ev_ghost, c->comm_stream));
+        a.chunk_mode = 1;
+        k_dd_fused<C, MODE, STAGES><<<dim3(c->fus_grid.x, c->fus_split_chunks, 1), c->fus_block, smem, c->stream>>>(a);
+        KCHECK();
+        CU(cudaStreamWaitEvent(c->stream, c->ev_ghost, 0));
+        c->launches += 2;
+    } else {
+        k_dd_fused<C, MODE, STAGES><<<c->fus_grid, c->fus_block, smem, c->stream>>>(a);
+        KCHECK();
+        c->launches++;
+    }
+    return SM_OK;
+}
+
+static bool fused_ok(const sm_ctx* c) { return c->use_fused && (!c->dist() || (c->rt == 1 && c->wx >= 4)); }
+
+// D D^dagger: one pass over HBM on a single tile, else D^dagger then D through the context's
+// scratch field (the reference's global DTEMP, dirac_operator.cpp:477-480)
+static int dev_DDdag(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, double m0) {
+    if (in == out) return fail(SM_ERR_ARG, "D D^dagger: in and out must not alias");
+    if (fused_ok(c)) return launch_fused<cplx, FUSED_PLAIN>(c, U, in, out, m0);
+    TRY(ensure_complex(c, &c->tmp));
+    TRY(dev_D(c, U, in, c->tmp, m0, true));
+    return dev_D(c, U, c->tmp, out, m0, false);
+}
+
+static int dev_dot_async(sm_ctx* c, const cplx* x, const cplx* y, double* d_out2) {
+    k_dot<<<c->flat_blocks_c, kBlock, 0, c->stream>>>(x, y, 2 * c->V, c->partials, c->tickets + TK_DOT,
+                                                      sum_target(c, d_out2));
+    KCHECK();
+    c->launches++;
+    return sum_finish(c, d_out2, 2);
+}
