@@ -271,8 +271,11 @@ def run_b200(args):
         return float(t.item())
 
     L = args.lattice
+    weak = args.scaling == "weak"
+    Lx = L * N if weak else L          # weak: every GPU keeps an L x L tile, the lattice grows along x
+    sites = Lx * L
     m0, beta = 0.0, 2.0
-    lat = sb.Lattice(L, L, device=local_rank, ranks_x=N, ranks_t=1, rank=rank, nccl_id=nccl_id)
+    lat = sb.Lattice(Lx, L, device=local_rank, ranks_x=N, ranks_t=1, rank=rank, nccl_id=nccl_id)
     halo = "none"
     if N > 1:
         halo = "nccl send/recv"
@@ -302,7 +305,7 @@ def run_b200(args):
     clocks = sampler.stop(t_begin, t_end, t_load + 0.2) if rank == 0 else None
     ms = max_over_ranks(ms)
     ms_per_step = ms / args.steps
-    value = (L * L) / (ms_per_step * 1e-3)
+    value = sites / (ms_per_step * 1e-3)
 
     peak, peak_src = measured_peaks()
     # dominant kernel: one k_dd_fused pass per step (on a split lattice the pass is an interior launch plus a
@@ -352,8 +355,8 @@ def run_b200(args):
                                             p_(x_p[1]), float(m0)))
     barrier()
     dd_call_s = max_over_ranks(time.perf_counter() - t1)
-    e2e = {"value": apps * (L * L) / e2e_s, "unit": UNIT,
-           "single_dd_call": {"value": (L * L) / dd_call_s, "unit": UNIT, "seconds": dd_call_s,
+    e2e = {"value": apps * sites / e2e_s, "unit": UNIT,
+           "single_dd_call": {"value": sites / dd_call_s, "unit": UNIT, "seconds": dd_call_s,
                               "note": "one sm_D_D_dagger_phi with host buffers: 96 B/site over PCIe for 192 B/site of "
                                       "algorithmic work, i.e. bound by the host link, not by the GPU"},
            "h2d_bytes_per_step": int(N * 2 * U_p.nbytes), "d2h_bytes_per_step": int(N * x_p.nbytes),
@@ -362,10 +365,10 @@ def run_b200(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"DD^dagger on {L}x{L}, beta=2, m0=0, hot-start links, Gaussian source "
-                               f"(BASELINE configs[3]); ranks_x={N}, ranks_t=1",
+        "config": {"workload": f"DD^dagger on {Lx}x{L}, beta=2, m0=0, hot-start links, Gaussian source "
+                               f"(BASELINE configs[3]{' tile per GPU' if weak else ''}); ranks_x={N}, ranks_t=1",
                    "l2": "inputs larger than L2 (each field %.0f MiB per GPU)" % (V * 32 / 2 ** 20),
                    "step": "one D D^dagger application over the whole lattice", "halo_exchange": halo},
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
@@ -385,7 +388,7 @@ def run_b200(args):
         dt = max_over_ranks(time.perf_counter() - t0)
         big["cg"] = {"solves_per_s": 1.0 / dt, "iterations": its, "converged": ok, "seconds": dt,
                      "GBs_per_gpu_320B": 320.0 * V * (its + 1) / dt / 1e9,
-                     "config": f"one (D D^dagger)^-1 solve on {L}x{L}, hot start, m0=0, tol 1e-10, device-resident"}
+                     "config": f"one (D D^dagger)^-1 solve on {Lx}x{L}, hot start, m0=0, tol 1e-10, device-resident"}
         if N == 1:
             # opt-in solver upgrade: same stopping criterion on the true residual, different iterate
             lat.set_solver(True)
@@ -407,7 +410,7 @@ def run_b200(args):
         dt = max_over_ranks(time.perf_counter() - t0)
         big["hmc"] = {"traj_per_s": 1.0 / dt, "seconds": dt, "dd_applications": int(r.dd_applications),
                       "cg_solves": int(r.cg_solves), "all_cg_converged": bool(r.cg_all_converged), "dH": r.dH,
-                      "config": f"one HMC trajectory on {L}x{L}, beta=2, m0=0, MD=10, tau=1, hot start, device-resident"}
+                      "config": f"one HMC trajectory on {Lx}x{L}, beta=2, m0=0, MD=10, tau=1, hot start, device-resident"}
         line["extra"] = {f"lattice_{L}": big}
         if N == 1:
             line["extra"].update(extra_metrics(sb, args))
@@ -475,6 +478,8 @@ def main():
     ap.add_argument("--ref-lattice", type=int, default=2048)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--skip-extra", action="store_true")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default): the 8192^2 lattice of configs[3] split over N GPUs; weak: an 8192^2 tile per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
