@@ -15,9 +15,10 @@ for who in b200 reference; do
   printf "$PARAMS" | "$exe" > out.txt 2> err.txt
   rc=$?
   t1=$(date +%s.%N)
-  ep=$(grep "Average plaquette" out.txt | sed 's/.*Ep = \([^ ]*\).*/\1/')
+  ep=$(grep "Average plaquette" out.txt | sed 's/.*: Ep = \([^ ]*\) dEp = \(.*\)/\1/')
+  dep=$(grep "Average plaquette" out.txt | sed 's/.*: Ep = \([^ ]*\) dEp = \(.*\)/\2/')
   acc=$(grep "Acceptance rate" out.txt | sed 's/.*: //')
   ex=$(grep "Execution time" out.txt | sed 's/.*= \([^ ]*\) s/\1/')
-  echo "{\"impl\": \"$who\", \"rc\": $rc, \"wall_s\": $(echo "$t1 - $t0" | bc), \"execution_time_s\": ${ex:-null}, \"Ep\": ${ep:-null}, \"acceptance\": ${acc:-null}, \"trajectories\": 100, \"simdata_lines\": $(cat 2D_U1_64x64_m00_SimData.txt 2>/dev/null | wc -l)}"
+  echo "{\"impl\": \"$who\", \"rc\": $rc, \"wall_s\": $(python3 -c "print(round($t1 - $t0, 3))"), \"execution_time_s\": ${ex:-null}, \"Ep\": ${ep:-null}, \"dEp\": ${dep:-null}, \"acceptance\": ${acc:-null}, \"trajectories\": 100, \"simdata_lines\": $(cat 2D_U1_64x64_m00_SimData.txt 2>/dev/null | wc -l)}"
   cd /; rm -rf "$d"
 done
