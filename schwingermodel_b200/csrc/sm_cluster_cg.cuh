@@ -6,7 +6,8 @@
 // entire solve: r, d and the links the site needs stay in REGISTERS, neighbours exchange
 // pre-projected half-spinors (each site publishes 4 complex numbers per stencil, the same rank-1
 // trick as the halo exchange), and the two global sums of an iteration are reduced in-kernel.
-// One iteration = 2 exchanges + 2 sums = 4 barriers; nothing is re-read from HBM.
+// One iteration = 2 exchanges + 2 sums in 3 barriers (the exchange of r shares its barrier with the
+// |r|^2 sum); nothing is re-read from HBM.
 //
 // Two transports for the exchange/barrier, same body:
 //   ClusterComm : one thread-block cluster (<= 16 CTAs x 256 threads = 4096 sites, e.g. 64 x 64,
@@ -76,9 +77,10 @@ struct ClusterComm {
     __device__ void barrier() { cluster.sync(); }
 
     // sum over all threads of the cluster, identical result everywhere: warp shuffle -> CTA partial in
-    // shared memory -> cluster barrier -> every warp adds the <= 16 CTA partials (one DSMEM load per lane)
+    // shared memory -> [barrier] -> every warp adds the <= 16 CTA partials (one DSMEM load per lane).
+    // Split in two so a caller can share the barrier with a half-spinor exchange.
     template <int NV>
-    __device__ void sum(int slot, double (&v)[NV]) {
+    __device__ void sum_begin(int slot, double (&v)[NV]) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         constexpr int W = kThreads / 32;
 #pragma unroll
@@ -95,7 +97,10 @@ struct ClusterComm {
                 if (lane == 0) sh->wsum[slot][j] = x;
             }
         }
-        cluster.sync();
+    }
+    template <int NV>
+    __device__ void sum_end(int slot, double (&v)[NV]) {
+        const int lane = threadIdx.x & 31;
         const int nb = (int)cluster.num_blocks();
 #pragma unroll
         for (int j = 0; j < NV; j++) {
@@ -105,6 +110,12 @@ struct ClusterComm {
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             v[j] = acc;
         }
+    }
+    template <int NV>
+    __device__ void sum(int slot, double (&v)[NV]) {
+        sum_begin<NV>(slot, v);
+        cluster.sync();
+        sum_end<NV>(slot, v);
     }
 };
 
@@ -149,10 +160,10 @@ struct GridComm {
         __syncthreads();
     }
 
-    // warp shuffle -> CTA partial (shared) -> L2 -> grid barrier -> every warp adds the <= 160 CTA
+    // warp shuffle -> CTA partial (shared) -> L2 -> [grid barrier] -> every warp adds the <= 160 CTA
     // partials with independent loads, in a fixed order
     template <int NV>
-    __device__ void sum(int slot, double (&v)[NV]) {
+    __device__ void sum_begin(int slot, double (&v)[NV]) {
         __shared__ double wpart[2][kThreads / 32];
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         constexpr int W = kThreads / 32;
@@ -171,7 +182,11 @@ struct GridComm {
                 if (lane == 0) __stcg(&wsum[(size_t)(slot * 2 + j) * nb + blockIdx.x], x);
             }
         }
-        barrier();
+    }
+    template <int NV>
+    __device__ void sum_end(int slot, double (&v)[NV]) {
+        const int lane = threadIdx.x & 31;
+        const int nb = (int)gridDim.x;
 #pragma unroll
         for (int j = 0; j < NV; j++) {
             const double* part = wsum + (size_t)(slot * 2 + j) * nb;
@@ -183,6 +198,12 @@ struct GridComm {
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             v[j] = acc;
         }
+    }
+    template <int NV>
+    __device__ void sum(int slot, double (&v)[NV]) {
+        sum_begin<NV>(slot, v);
+        barrier();
+        sum_end<NV>(slot, v);
     }
 };
 
@@ -215,7 +236,11 @@ __device__ __forceinline__ void resident_cg(const ResidentCgArgs& a, Comm& comm)
         f1 = a.phi[V + n];
     }
 
-    // one stencil application = publish the four half-spinors of (p0,p1), barrier, gather
+    // A stencil application = every site publishes four half-spinors of its spinor, a barrier, every site
+    // fetches the four that point at it and combines them with its own value.
+    struct Halves {
+        cplx tp, xp, tm, xm;
+    };
     auto publish = [&](auto hop_tag, int buf, cplx p0, cplx p1) {
         using H = decltype(hop_tag);
         comm.put(buf, 0, H::from_tp(p0, p1));
@@ -223,51 +248,65 @@ __device__ __forceinline__ void resident_cg(const ResidentCgArgs& a, Comm& comm)
         comm.put(buf, 2, H::from_xp(p0, p1));
         comm.put(buf, 3, cmulc(u1, H::from_xm(p0, p1)));
     };
-    auto gather = [&](auto hop_tag, int buf, cplx p0, cplx p1, cplx& o0, cplx& o1) {
+    auto fetch = [&](int buf) {
+        Halves h;
+        h.tp = comm.get_tp(buf);
+        h.xp = comm.get_xp(buf);
+        h.tm = comm.get_tm(buf);
+        h.xm = comm.get_xm(buf);
+        return h;
+    };
+    auto combine = [&](auto hop_tag, const Halves& h, cplx p0, cplx p1, cplx& o0, cplx& o1) {
         using H = decltype(hop_tag);
         cplx a0, a1;
-        H::add_tp(cscale(sR, cmul(u0, comm.get_tp(buf))), a0, a1);
-        H::add_xp(cmul(u1, comm.get_xp(buf)), a0, a1);
-        H::add_tm(cscale(sL, comm.get_tm(buf)), a0, a1);
-        H::add_xm(comm.get_xm(buf), a0, a1);
+        H::add_tp(cscale(sR, cmul(u0, h.tp)), a0, a1);
+        H::add_xp(cmul(u1, h.xp), a0, a1);
+        H::add_tm(cscale(sL, h.tm), a0, a1);
+        H::add_xm(h.xm, a0, a1);
         o0 = make_double2(a.mass * p0.x - 0.5 * a0.x, a.mass * p0.y - 0.5 * a0.y);
         o1 = make_double2(a.mass * p1.x - 0.5 * a1.x, a.mass * p1.y - 0.5 * a1.y);
     };
-    // out = D D^dagger p : two exchanges, two barriers.  Buffer 0 carries psi, buffer 1 carries t;
-    // a buffer is rewritten only after a later barrier than the one its readers waited on.
-    auto dd = [&](cplx p0, cplx p1, cplx& o0, cplx& o1) {
-        cplx t0, t1;
-        publish(Hop<true>{}, 0, p0, p1);
-        comm.barrier();
-        gather(Hop<true>{}, 0, p0, p1, t0, t1);
-        publish(Hop<false>{}, 1, t0, t1);
-        comm.barrier();
-        gather(Hop<false>{}, 1, t0, t1, o0, o1);
-    };
+    // Buffer 0 carries the halves of psi / r, buffer 1 those of t; a buffer (and a sum slot) is rewritten
+    // only after a later barrier than the one its readers waited on.
 
     // x = phi ; r = phi - D D^dagger phi ; d = r   (conjugate_gradient.cpp:16-24).
-    // x lives in global memory: it is only ever updated in place, never exchanged.
-    cplx r0, r1, d0, d1, A0, A1;
-    dd(f0, f1, A0, A1);
+    cplx r0, r1, d0, d1, A0, A1, t0, t1;
+    publish(Hop<true>{}, 0, f0, f1);
+    comm.barrier();
+    combine(Hop<true>{}, fetch(0), f0, f1, t0, t1);
+    publish(Hop<false>{}, 1, t0, t1);
+    comm.barrier();
+    combine(Hop<false>{}, fetch(1), t0, t1, A0, A1);
     r0 = csub(f0, A0);
     r1 = csub(f1, A1);
     if (!active) r0 = r1 = zero;
     d0 = r0;
     d1 = r1;
     cplx xr0 = f0, xr1 = f1;                            // x when it is kept in registers
-    if (!Comm::kXInRegisters && active) {
+    if (!Comm::kXInRegisters && active) {               // else x lives in L2: only ever updated in place
         a.x[n] = f0;
         a.x[V + n] = f1;
     }
     double s2[2] = {f0.x * f0.x + f0.y * f0.y + f1.x * f1.x + f1.y * f1.y,
                     r0.x * r0.x + r0.y * r0.y + r1.x * r1.x + r1.y * r1.y};
-    comm.template sum<2>(1, s2);
+    // the same barrier serves the two sums and the exchange of the halves of d_0 = r_0
+    comm.template sum_begin<2>(1, s2);
+    publish(Hop<true>{}, 0, r0, r1);
+    comm.barrier();
+    comm.template sum_end<2>(1, s2);
+    Halves Hd = fetch(0);                               // the neighbours' halves of d_k, kept across iterations
     const double phi_norm = sqrt(s2[0]);
     double rr = s2[1];
 
+    // Three barriers per iteration: the halves of d_{k+1} = r_{k+1} + beta d_k are formed locally from the
+    // exchanged halves of r_{k+1} (the projections are linear) and the kept halves of d_k, so the exchange
+    // of r shares its barrier with the |r|^2 sum.
     int k = 0, converged = 0;
     while (k < a.max_iter) {
-        dd(d0, d1, A0, A1);
+        combine(Hop<true>{}, Hd, d0, d1, t0, t1);       // t = D^dagger d
+        publish(Hop<false>{}, 1, t0, t1);
+        comm.barrier();
+        combine(Hop<false>{}, fetch(1), t0, t1, A0, A1);   // Ad = D t
         if (!active) A0 = A1 = zero;
         // alpha = r_norm2 / dot(d, Ad)   (:33)
         const cplx q0 = cmul_conj(d0, A0), q1 = cmul_conj(d1, A1);
@@ -289,12 +328,20 @@ __device__ __forceinline__ void resident_cg(const ResidentCgArgs& a, Comm& comm)
         r0 = csub(r0, cmul(alpha, A0));                 // r -= alpha Ad  (:37-41)
         r1 = csub(r1, cmul(alpha, A1));
         double e2[1] = {r0.x * r0.x + r0.y * r0.y + r1.x * r1.x + r1.y * r1.y};
-        comm.template sum<1>(1, e2);
+        comm.template sum_begin<1>(1, e2);
+        publish(Hop<true>{}, 0, r0, r1);
+        comm.barrier();
+        comm.template sum_end<1>(1, e2);
         if (sqrt(e2[0]) < a.tol * phi_norm) {           // :45
             converged = 1;
             break;
         }
         const double beta = e2[0] / rr;                 // :51-59
+        const Halves Hr = fetch(0);
+        Hd.tp = make_double2(Hd.tp.x * beta + Hr.tp.x, Hd.tp.y * beta + Hr.tp.y);
+        Hd.xp = make_double2(Hd.xp.x * beta + Hr.xp.x, Hd.xp.y * beta + Hr.xp.y);
+        Hd.tm = make_double2(Hd.tm.x * beta + Hr.tm.x, Hd.tm.y * beta + Hr.tm.y);
+        Hd.xm = make_double2(Hd.xm.x * beta + Hr.xm.x, Hd.xm.y * beta + Hr.xm.y);
         d0 = make_double2(d0.x * beta + r0.x, d0.y * beta + r0.y);
         d1 = make_double2(d1.x * beta + r1.x, d1.y * beta + r1.y);
         rr = e2[0];
