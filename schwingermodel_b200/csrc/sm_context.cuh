@@ -110,8 +110,8 @@ struct sm_ctx {
     long long launches = 0;
 
     // launch geometry
-    dim3 wil_block, wil_grid;
-    int rows_per_block = 0;
+    dim3 wil_block, wil_grid, wil_grid_plain;
+    int rows_per_block = 0, rows_per_block_plain = 0;
     dim3 fus_block, fus_grid;   // one-pass D D^dagger (sm_fused.cuh)
     int fus_rows = 0, fus_cols = 0;
     int fus_rb = 8, fus_split_rows = 0, fus_split_chunks = 0;   // interior/boundary launch split (split lattice)
@@ -242,16 +242,25 @@ static int ctx_common_init(sm_ctx* c) {
     const int TX = kBlock / TT;
     c->wil_block = dim3(TT, TX, 1);
     const int nT = (c->wt + TT - 1) / TT;
-    int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wilson<false, WILSON_DOT>, kBlock, 0));
-    if (occ < 1) occ = 1;
-    const int target = c->sm_count * occ;
-    const int steps = (c->wx + TX - 1) / TX;
-    int GY = std::max(1, std::min(steps, target / nT));
-    int rows = ((c->wx + GY - 1) / GY + TX - 1) / TX * TX;
-    GY = (c->wx + rows - 1) / rows;
-    c->rows_per_block = rows;
-    c->wil_grid = dim3(nT, GY, 1);
+    // persistent grids: one wave of resident blocks, sized per kernel variant (the plain stencil needs 40
+    // registers and fits 6 blocks per SM, the variants with fused sums 58-60 and fit 4)
+    auto grid_for = [&](int occ, dim3* grid, int* rows_out) {
+        if (occ < 1) occ = 1;
+        if (const char* e = getenv("SM_WILSON_BLOCKS_PER_SM")) occ = std::max(1, atoi(e));
+        const int target = c->sm_count * occ;
+        const int steps = (c->wx + TX - 1) / TX;
+        int GY = std::max(1, std::min(steps, target / nT));
+        int rows = ((c->wx + GY - 1) / GY + TX - 1) / TX * TX;
+        GY = (c->wx + rows - 1) / rows;
+        *rows_out = rows;
+        *grid = dim3(nT, GY, 1);
+    };
+    int occ_plain = 0, occ_sum = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_plain, k_wilson<false, WILSON_PLAIN>, kBlock, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sum, k_wilson<false, WILSON_DOT>, kBlock, 0));
+    grid_for(occ_plain, &c->wil_grid_plain, &c->rows_per_block_plain);
+    grid_for(occ_sum, &c->wil_grid, &c->rows_per_block);
+    const int GY = std::max(c->wil_grid.y, c->wil_grid_plain.y);
 
     // one-pass D D^dagger: strips of <= BT-4 columns, chunks of rows.  Large lattices: ~8 waves of
     // blocks with >= 64 rows each (4 warm-up rows per chunk); mid-size: one resident wave.

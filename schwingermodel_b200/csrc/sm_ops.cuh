@@ -22,7 +22,7 @@ static int launch_wilson(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, do
     a.wx = c->wx;
     a.wt = c->wt;
     a.V = c->V;
-    a.rows_per_block = c->rows_per_block;
+    a.rows_per_block = (MODE == WILSON_PLAIN) ? c->rows_per_block_plain : c->rows_per_block;
     a.mass = m0 + 2;
     a.sR_edge = c->sR_edge();
     a.sL_edge = c->sL_edge();
@@ -34,7 +34,7 @@ static int launch_wilson(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, do
     a.ticket = c->tickets + TK_WILSON;
     a.sums_out = sums_out;
     a.done = done;
-    k_wilson<DAG, MODE><<<c->wil_grid, c->wil_block, 0, c->stream>>>(a);
+    k_wilson<DAG, MODE><<<(MODE == WILSON_PLAIN) ? c->wil_grid_plain : c->wil_grid, c->wil_block, 0, c->stream>>>(a);
     KCHECK();
     c->launches++;
     return SM_OK;
