@@ -242,10 +242,14 @@ static int ctx_common_init(sm_ctx* c) {
     const int TX = kBlock / TT;
     c->wil_block = dim3(TT, TX, 1);
     const int nT = (c->wt + TT - 1) / TT;
-    // persistent grids: one wave of resident blocks, sized per kernel variant (the plain stencil needs 40
-    // registers and fits 6 blocks per SM, the variants with fused sums 58-60 and fit 4)
+    // grids sized per kernel variant (the plain stencil needs 40 registers and fits 6 blocks per SM, the
+    // variants with fused sums 58-60 and fit 4): one resident wave on lattices that live in L2, 8 waves of
+    // shorter row runs (~70 rows at 8192^2) on large ones -- measured 6.41 vs 5.77 TB/s there
+    // (profiles/r01_sweep_wilson.txt)
+    const int waves = ((long long)c->wx * c->wt >= (1LL << 22)) ? 8 : 1;
     auto grid_for = [&](int occ, dim3* grid, int* rows_out) {
         if (occ < 1) occ = 1;
+        occ *= waves;
         if (const char* e = getenv("SM_WILSON_BLOCKS_PER_SM")) occ = std::max(1, atoi(e));
         const int target = c->sm_count * occ;
         const int steps = (c->wx + TX - 1) / TX;
