@@ -21,6 +21,8 @@
  *   - in a distributed context (ranks_x*ranks_t > 1, one process per GPU) every call that touches
  *     neighbours or global sums is collective, like the reference's MPI calls; host buffers hold
  *     this rank's width_x*width_t tile (n = x_local*width_t + t_local), as in the reference.
+ *   - like the reference (single-threaded per rank, global scratch), a context is not re-entrant: one thread
+ *     drives one context at a time; different contexts (GPUs) may be driven by different threads.
  *   - there is no CPU fallback: without a usable CUDA device sm_create fails with SM_ERR_CUDA.
  */
 #ifndef SCHWINGER_B200_H

@@ -167,6 +167,8 @@ int sm_destroy(sm_ctx* c) {
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->comm_stream);
     cudaEventDestroy(c->ev_ready);
+    cudaEventDestroy(c->ev_t0);
+    cudaEventDestroy(c->ev_t1);
     cudaEventDestroy(c->ev_ghost);
     delete c;
     return SM_OK;
@@ -561,20 +563,15 @@ int sm_hmc_trajectory(sm_ctx* c, sm_traj_result* out) {
     if (!c->hmc_has_fields) return fail(SM_ERR_STATE, "sm_hmc_refresh or sm_hmc_inject first");
     if (c->hp.md_steps < 1) return fail(SM_ERR_STATE, "sm_hmc_configure first");
     TrajAcc acc;
-    cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0));
-    CU(cudaEventCreate(&e1));
-    CU(cudaEventRecord(e0, c->stream));
+    CU(cudaEventRecord(c->ev_t0, c->stream));
     TRY(dev_D(c, c->U, c->chi, c->phi, c->hp.m0, false));                 // hmc.cpp:160
     TRY(hmc_leapfrog(c, &acc));                                           // hmc.cpp:161
     TRY(hmc_hamiltonian_async(c, c->Up, c->pip, c->phi, 0, &acc));        // hmc.cpp:162 (new)
     TRY(hmc_hamiltonian_async(c, c->U, c->pi, c->phi, 5, &acc));          //             (old)
-    CU(cudaEventRecord(e1, c->stream));
+    CU(cudaEventRecord(c->ev_t1, c->stream));
     TRY(fetch_sums(c, 10));
     float ms = 0.f;
-    CU(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
+    CU(cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1));
     const double* s = c->h->sums;
     out->H_new = hamiltonian_from(s);
     out->H_old = hamiltonian_from(s + 5);

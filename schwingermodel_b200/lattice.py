@@ -62,9 +62,9 @@ class DeviceField:
         return out
 
     def free(self):
-        if self.ptr:
+        if self.ptr and getattr(self.lat, "ctx", None):     # sm_destroy already released every field of a closed lattice
             check(self.lat.lib.sm_field_free(self.lat.ctx, self.ptr))
-            self.ptr = None
+        self.ptr = None
 
 
 class Lattice:
