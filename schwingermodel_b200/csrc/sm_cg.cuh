@@ -18,7 +18,7 @@ static int dev_cg_twopass(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, do
     CgState* st = c->cg;
     const int* done = &st->done;
 
-    k_cg_reset<<<1, 1, 0, c->stream>>>(st, tol);
+    k_cg_reset<<<1, 1, 0, c->stream>>>(st, tol, max_iter);
     c->launches++;
     // Ad = DD^dagger phi ; r = phi - Ad ; d = r ; x = phi ; |phi|^2, |r|^2
     TRY((launch_wilson<true, WILSON_PLAIN>(c, U, phi, c->tmp, m0)));
@@ -104,7 +104,7 @@ static int cg_fused_loop(sm_ctx* c, const C* U, C* r, C* x, C* dbuf0, C* dbuf1, 
     const bool graphs = c->use_graphs && !c->dist() && max_iter > batch;
     if (graphs) {
         for (auto& g : c->cg_graphs)
-            if (g.U == (const void*)U && g.x == (const void*)x && g.m0 == m0 && g.max_iter == max_iter) {
+            if (g.U == (const void*)U && g.x == (const void*)x && g.m0 == m0) {
                 exec = g.exec;
                 graph_kernels = g.kernels;
             }
@@ -119,7 +119,7 @@ static int cg_fused_loop(sm_ctx* c, const C* U, C* r, C* x, C* dbuf0, C* dbuf1, 
         int rc = SM_OK;
         for (int i = 0; i < batch && rc == SM_OK; i++) rc = iteration(1 + i);
         if (rc == SM_OK) {
-            k_cg_check_dev<<<1, 1, 0, c->stream>>>(st, max_iter);
+            k_cg_check_dev<<<1, 1, 0, c->stream>>>(st);
             c->launches++;
         }
         cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
@@ -133,7 +133,7 @@ static int cg_fused_loop(sm_ctx* c, const C* U, C* r, C* x, C* dbuf0, C* dbuf1, 
             cudaGraphExecDestroy(c->cg_graphs.front().exec);
             c->cg_graphs.erase(c->cg_graphs.begin());
         }
-        c->cg_graphs.push_back({(const void*)U, (const void*)x, m0, max_iter, exec, graph_kernels});
+        c->cg_graphs.push_back({(const void*)U, (const void*)x, m0, exec, graph_kernels});
     }
     for (;;) {
         if (exec != nullptr && k + batch <= max_iter) {
@@ -143,7 +143,7 @@ static int cg_fused_loop(sm_ctx* c, const C* U, C* r, C* x, C* dbuf0, C* dbuf1, 
         } else {
             const int k_end = std::min(max_iter, k + batch);
             for (; k < k_end; k++) TRY(iteration(k));
-            k_cg_check_dev<<<1, 1, 0, c->stream>>>(st, max_iter);
+            k_cg_check_dev<<<1, 1, 0, c->stream>>>(st);
             KCHECK();
             c->launches++;
         }
@@ -173,7 +173,7 @@ static int dev_cg_fused(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, doub
     TRY(ensure_complex(c, &c->cg_d2));
     TRY(ensure_complex(c, &c->cg_Ad));
     CgState* st = c->cg;
-    k_cg_reset<<<1, 1, 0, c->stream>>>(st, c->tol);
+    k_cg_reset<<<1, 1, 0, c->stream>>>(st, c->tol, c->max_iter);
     c->launches++;
     // x = phi ; r = phi - D D^dagger phi ; |phi|^2, |r|^2   (d_0 = r_0 is formed by the first pass)
     TRY((launch_wilson<true, WILSON_PLAIN>(c, U, phi, c->tmp, m0)));
@@ -228,11 +228,11 @@ static int dev_cg_mixed(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, doub
         // do not over-solve the last cycle; single precision stalls near 1e-6
         const double need = 0.5 * c->tol * std::sqrt(pp) / std::sqrt(rr);
         const double delta = std::min(0.1, std::max(1e-5, need));
-        k_mixed_begin<<<1, 1, 0, c->stream>>>(c->cg, c->sums + 12, delta);
+        const int inner_max = std::max(1, c->max_iter - total);
+        k_mixed_begin<<<1, 1, 0, c->stream>>>(c->cg, c->sums + 12, delta, inner_max);
         KCHECK();
         c->launches++;
-        TRY(cg_fused_loop<cplxf>(c, c->mx_U, c->mx_r, c->mx_e, c->mx_d0, c->mx_d1, c->mx_Ad, m0,
-                                 std::max(1, c->max_iter - total)));
+        TRY(cg_fused_loop<cplxf>(c, c->mx_U, c->mx_r, c->mx_e, c->mx_d0, c->mx_d1, c->mx_Ad, m0, inner_max));
         total += c->h->cg[0].converged ? c->h->cg[0].iters + 1 : c->h->cg[0].iters;
         k_mixed_correct<<<c->flat_blocks_c, kBlock, 0, c->stream>>>(x, c->mx_e, n_elems);
         KCHECK();

@@ -173,7 +173,6 @@ struct sm_ctx {
         const void* U;
         const void* x;
         double m0;
-        int max_iter;
         cudaGraphExec_t exec;
         int kernels;
     };

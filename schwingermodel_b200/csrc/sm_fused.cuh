@@ -425,7 +425,8 @@ __global__ void __launch_bounds__(kBlock) k_mixed_correct(cplx* __restrict__ x, 
 }
 
 // inner solve starts from e = 0: r_in = r_outer, |r_in|^2 known; stop at |r_in| < delta |r_outer|
-__global__ void k_mixed_begin(CgState* st, const double* sums /* |phi|^2, |r|^2 */, double delta) {
+__global__ void k_mixed_begin(CgState* st, const double* sums /* |phi|^2, |r|^2 */, double delta, int max_iter) {
+    st->max_iter = max_iter;
     st->done = 0;
     st->iters = 0;
     st->converged = 0;

@@ -60,8 +60,8 @@ struct CgState {
     int pending;        // fused path: an x update is owed
     int pending_buf;    // ... with d in ping-pong buffer 0/1
     int k;              // iteration counter kept on the device (one-pass path: kernels are replayed from a CUDA graph)
-    int pad;
-    double tol;         // one-pass path: relative tolerance of the running solve (kept here so graphs do not bake it)
+    int max_iter;       // one-pass path: iteration limit of the running solve (kept here so graphs do not bake it)
+    double tol;         // ... and its relative tolerance
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -359,9 +359,9 @@ __global__ void k_cg_check(CgState* st, int k, double tol, int max_iter) {
 }
 
 // the same with the device-side iteration counter (one-pass path)
-__global__ void k_cg_check_dev(CgState* st, int max_iter) {
+__global__ void k_cg_check_dev(CgState* st) {
     if (st->done) return;
-    const int k = st->k;
+    const int k = st->k, max_iter = st->max_iter;
     if (cg_converged(st, k & 1, st->tol)) {
         st->iters = k - 1;
         st->converged = 1;
@@ -373,8 +373,9 @@ __global__ void k_cg_check_dev(CgState* st, int max_iter) {
     }
 }
 
-__global__ void k_cg_reset(CgState* st, double tol) {
+__global__ void k_cg_reset(CgState* st, double tol, int max_iter) {
     st->tol = tol;
+    st->max_iter = max_iter;
     st->done = 0;
     st->iters = 0;
     st->converged = 0;
