@@ -46,7 +46,6 @@ static int dev_D(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, double m0,
     return launch_wilson<false, WILSON_PLAIN>(c, U, in, out, m0);
 }
 
-// D D^dagger via the context's scratch field (the reference's global DTEMP, dirac_operator.cpp:477-480)
 // ---- peer-memory window ------------------------------------------------------------------------
 static size_t win_ghost_elems(const sm_ctx* c) { return 4 * (size_t)c->wt; }
 static cplx* win_ghost(const sm_ctx* c, void* base, int kind, int parity, int side) {
