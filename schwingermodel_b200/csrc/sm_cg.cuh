@@ -327,10 +327,67 @@ static int dev_cg_coop(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, doubl
     return resident_finish(c, converged, iterations);
 }
 
+// several sites per thread on the same cooperative grid (k_cg_coop_multi): the smallest slot count whose full grid
+// holds the lattice, 0 if none does
+template <int S>
+static int coop_multi_blocks_per_sm(sm_ctx* c) {
+    const size_t smem = coop_multi_smem(S);
+    if (cudaFuncSetAttribute(k_cg_coop_multi<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_coop_multi<S>, kCoopThreads, smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return per_sm;
+}
+
+static int coop_multi_slots(sm_ctx* c) {
+    if (c->coop_slots < 0) {
+        c->coop_slots = 0;
+        int coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
+        const int per_sm[kCoopMaxSlots + 1] = {0, 0, coop ? coop_multi_blocks_per_sm<2>(c) : 0,
+                                               coop ? coop_multi_blocks_per_sm<3>(c) : 0,
+                                               coop ? coop_multi_blocks_per_sm<4>(c) : 0};
+        for (int s = 2; s <= std::min(kCoopMaxSlots, c->coop_max_slots); s++) {
+            const long long blocks = ((long long)c->V + (long long)s * kCoopThreads - 1) / ((long long)s * kCoopThreads);
+            if (per_sm[s] > 0 && blocks <= (long long)per_sm[s] * c->sm_count) {
+                c->coop_slots = s;
+                break;
+            }
+        }
+    }
+    return c->coop_slots;
+}
+
+static int dev_cg_coop_multi(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, int* converged, int* iterations) {
+    ResidentCgArgs a;
+    TRY(resident_args(c, U, phi, x, m0, &a));
+    const int S = c->coop_slots;
+    const int blocks = (c->V + S * kCoopThreads - 1) / (S * kCoopThreads);
+    if (!c->coop_hop) {
+        TRY(dev_alloc(&c->coop_hop, (size_t)8 * c->V));
+        TRY(dev_alloc(&c->coop_wsum, (size_t)4 * ((c->V + kCoopThreads - 1) / kCoopThreads) * (kCoopThreads / 32)));
+        TRY(dev_alloc(&c->coop_bar, (size_t)32));
+    }
+    CU(cudaMemsetAsync(c->coop_bar, 0, sizeof(unsigned int) * 32, c->stream));
+    a.hop = c->coop_hop;
+    a.wsum = c->coop_wsum;
+    a.bar = c->coop_bar;
+    void* params[] = {&a};
+    const void* fn = S == 2 ? (const void*)k_cg_coop_multi<2> : S == 3 ? (const void*)k_cg_coop_multi<3> : (const void*)k_cg_coop_multi<4>;
+    CU(cudaLaunchCooperativeKernel(fn, dim3(blocks, 1, 1), dim3(kCoopThreads, 1, 1), params, coop_multi_smem(S), c->stream));
+    return resident_finish(c, converged, iterations);
+}
+
 static int dev_cg(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, int* converged, int* iterations) {
     if (c->use_cluster && !c->dist()) {
         if (c->V <= kClusterMaxCtas * kClusterThreads) return dev_cg_cluster(c, U, phi, x, m0, converged, iterations);
         if (c->V <= coop_capacity(c)) return dev_cg_coop(c, U, phi, x, m0, converged, iterations);
+        if (coop_multi_slots(c) > 0) return dev_cg_coop_multi(c, U, phi, x, m0, converged, iterations);
     }
     if (c->solver == SM_SOLVER_MIXED && fused_ok(c) && !c->dist()) return dev_cg_mixed(c, U, phi, x, m0, converged, iterations);
     if (fused_ok(c)) return dev_cg_fused(c, U, phi, x, m0, converged, iterations);

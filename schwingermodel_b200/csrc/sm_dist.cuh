@@ -24,8 +24,9 @@ static int sum_finish(sm_ctx* c, double* glob, int n) {
     return allreduce_sums(c, c->sums_loc, glob, n);
 }
 
+// the four projected halo lines of `in` into the send buffers (k_pack_halo)
 template <bool DAG>
-static int exchange_spinor_halo(sm_ctx* c, const cplx* U, const cplx* in, const int* done) {
+static int pack_spinor_halo(sm_ctx* c, const cplx* U, const cplx* in, const int* done) {
     PackArgs p{};
     p.U = U;
     p.in = in;
@@ -41,18 +42,23 @@ static int exchange_spinor_halo(sm_ctx* c, const cplx* U, const cplx* in, const 
     k_pack_halo<DAG><<<(n + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(p);
     KCHECK();
     c->launches++;
+    return SM_OK;
+}
+
+// send buffers -> the neighbours' ghost lines (one grouped NCCL send/recv) on stream `st`
+static int exchange_spinor_lines(sm_ctx* c, cudaStream_t st) {
     NC(g_nccl.GroupStart());
     if (c->rt > 1) {
-        NC(g_nccl.Send(c->send_tm, 2 * (size_t)c->wx, ncclDouble, c->nb_tm, c->comm, c->stream));
-        NC(g_nccl.Send(c->send_tp, 2 * (size_t)c->wx, ncclDouble, c->nb_tp, c->comm, c->stream));
-        NC(g_nccl.Recv(c->g_tp, 2 * (size_t)c->wx, ncclDouble, c->nb_tp, c->comm, c->stream));
-        NC(g_nccl.Recv(c->g_tm, 2 * (size_t)c->wx, ncclDouble, c->nb_tm, c->comm, c->stream));
+        NC(g_nccl.Send(c->send_tm, 2 * (size_t)c->wx, ncclDouble, c->nb_tm, c->comm, st));
+        NC(g_nccl.Send(c->send_tp, 2 * (size_t)c->wx, ncclDouble, c->nb_tp, c->comm, st));
+        NC(g_nccl.Recv(c->g_tp, 2 * (size_t)c->wx, ncclDouble, c->nb_tp, c->comm, st));
+        NC(g_nccl.Recv(c->g_tm, 2 * (size_t)c->wx, ncclDouble, c->nb_tm, c->comm, st));
     }
     if (c->rx > 1) {
-        NC(g_nccl.Send(c->send_xm, 2 * (size_t)c->wt, ncclDouble, c->nb_xm, c->comm, c->stream));
-        NC(g_nccl.Send(c->send_xp, 2 * (size_t)c->wt, ncclDouble, c->nb_xp, c->comm, c->stream));
-        NC(g_nccl.Recv(c->g_xp, 2 * (size_t)c->wt, ncclDouble, c->nb_xp, c->comm, c->stream));
-        NC(g_nccl.Recv(c->g_xm, 2 * (size_t)c->wt, ncclDouble, c->nb_xm, c->comm, c->stream));
+        NC(g_nccl.Send(c->send_xm, 2 * (size_t)c->wt, ncclDouble, c->nb_xm, c->comm, st));
+        NC(g_nccl.Send(c->send_xp, 2 * (size_t)c->wt, ncclDouble, c->nb_xp, c->comm, st));
+        NC(g_nccl.Recv(c->g_xp, 2 * (size_t)c->wt, ncclDouble, c->nb_xp, c->comm, st));
+        NC(g_nccl.Recv(c->g_xm, 2 * (size_t)c->wt, ncclDouble, c->nb_xm, c->comm, st));
     }
     NC(g_nccl.GroupEnd());
     return SM_OK;

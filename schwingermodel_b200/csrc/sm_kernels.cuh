@@ -104,6 +104,9 @@ struct WilsonArgs {
     unsigned int* ticket;
     double* sums_out;
     const int* done;   // CG early-out flag (null outside CG)
+    int interior_only;     // split lattice with overlap: skip the sites that read ghost lines ...
+    int boundary_blocks;   // ... k_wilson_boundary (this many blocks) computes them and joins the reduction
+    int interior_blocks;   // (boundary launch) blocks of the interior launch
 };
 
 template <bool DAG>
@@ -185,6 +188,40 @@ __device__ __forceinline__ void wilson_site(const WilsonArgs& a, int x, int t, c
     o1 = make_double2(a.mass * c1.x - 0.5 * acc1.x, a.mass * c1.y - 0.5 * acc1.y);
 }
 
+// what a stencil pass does with the site's result besides (or instead of) storing it
+template <int MODE, int NS>
+__device__ __forceinline__ void wilson_epilogue(const WilsonArgs& a, int n, cplx o0, cplx o1, double (&acc)[NS]) {
+    if (MODE == WILSON_PLAIN) {
+        a.out[n] = o0;
+        a.out[a.V + n] = o1;
+    } else if (MODE == WILSON_DOT) {
+        // Ad = D t, partial of dot(d, Ad) = sum d conj(Ad)   (conjugate_gradient.cpp:32-33)
+        a.out[n] = o0;
+        a.out[a.V + n] = o1;
+        const cplx d0 = ld_stream(a.aux + n), d1 = ld_stream(a.aux + a.V + n);
+        const cplx p0 = cmul_conj(d0, o0), p1 = cmul_conj(d1, o1);
+        acc[0] += p0.x + p1.x;
+        acc[NS - 1] += p0.y + p1.y;
+    } else {
+        // x = phi ; r = phi - DD^dagger phi ; d = r   (conjugate_gradient.cpp:16-24)
+        const cplx f0 = ld_stream(a.aux + n), f1 = ld_stream(a.aux + a.V + n);
+        const cplx r0 = csub(f0, o0), r1 = csub(f1, o1);
+        a.x[n] = f0;
+        a.x[a.V + n] = f1;
+        a.r[n] = r0;
+        a.r[a.V + n] = r1;
+        a.d[n] = r0;
+        a.d[a.V + n] = r1;
+        acc[0] += f0.x * f0.x + f0.y * f0.y + f1.x * f1.x + f1.y * f1.y;        // |phi|^2
+        acc[NS - 1] += r0.x * r0.x + r0.y * r0.y + r1.x * r1.x + r1.y * r1.y;   // |r|^2
+    }
+}
+
+// a site whose stencil reads a ghost line (only on a split lattice)
+__device__ __forceinline__ bool wilson_on_boundary(const WilsonArgs& a, int x, int t) {
+    return (a.g_tp != nullptr && (t == 0 || t == a.wt - 1)) || (a.g_xp != nullptr && (x == 0 || x == a.wx - 1));
+}
+
 template <bool DAG, int MODE>
 __global__ void __launch_bounds__(kBlock) k_wilson(const WilsonArgs a) {
     if (a.done != nullptr && *a.done) return;
@@ -199,38 +236,55 @@ __global__ void __launch_bounds__(kBlock) k_wilson(const WilsonArgs a) {
 
     if (t_ok) {
         for (int x = x_begin + threadIdx.y; x < x_end; x += blockDim.y) {
+            if (a.interior_only && wilson_on_boundary(a, x, t)) continue;   // k_wilson_boundary takes those
             cplx o0, o1;
             wilson_site<DAG>(a, x, t, o0, o1);
-            const int n = x * a.wt + t;
-            if (MODE == WILSON_PLAIN) {
-                a.out[n] = o0;
-                a.out[a.V + n] = o1;
-            } else if (MODE == WILSON_DOT) {
-                // Ad = D t, partial of dot(d, Ad) = sum d conj(Ad)   (conjugate_gradient.cpp:32-33)
-                a.out[n] = o0;
-                a.out[a.V + n] = o1;
-                const cplx d0 = ld_stream(a.aux + n), d1 = ld_stream(a.aux + a.V + n);
-                const cplx p0 = cmul_conj(d0, o0), p1 = cmul_conj(d1, o1);
-                acc[0] += p0.x + p1.x;
-                acc[1] += p0.y + p1.y;
-            } else {
-                // x = phi ; r = phi - DD^dagger phi ; d = r   (conjugate_gradient.cpp:16-24)
-                const cplx f0 = ld_stream(a.aux + n), f1 = ld_stream(a.aux + a.V + n);
-                const cplx r0 = csub(f0, o0), r1 = csub(f1, o1);
-                a.x[n] = f0;
-                a.x[a.V + n] = f1;
-                a.r[n] = r0;
-                a.r[a.V + n] = r1;
-                a.d[n] = r0;
-                a.d[a.V + n] = r1;
-                acc[0] += f0.x * f0.x + f0.y * f0.y + f1.x * f1.x + f1.y * f1.y;   // |phi|^2
-                acc[1] += r0.x * r0.x + r0.y * r0.y + r1.x * r1.x + r1.y * r1.y;   // |r|^2
-            }
+            wilson_epilogue<MODE, NS>(a, x * a.wt + t, o0, o1, acc);
         }
     }
     if (MODE != WILSON_PLAIN) {
-        if (grid_reduce<NS>(acc, a.partials, a.ticket)) {
+        const int nb = gridDim.x * gridDim.y;
+        if (grid_reduce<NS>(acc, a.partials, a.ticket, nb + a.boundary_blocks, blockIdx.y * gridDim.x + blockIdx.x)) {
             if (threadIdx.x == 0 && threadIdx.y == 0) {
+                a.sums_out[0] = acc[0];
+                a.sums_out[1] = acc[1];
+            }
+        }
+    }
+}
+
+// The sites of a split lattice that read ghost lines: columns t = 0 and wt-1 (split along t) and rows
+// x = 0 and wx-1 (split along x; their corner sites belong to the columns when both are split).  Runs on
+// the comm stream after the halo exchange while k_wilson(interior_only) computes everything else; the two
+// launches share one reduction (ticket and block numbering).
+template <bool DAG, int MODE>
+__global__ void __launch_bounds__(kBlock) k_wilson_boundary(const WilsonArgs a) {
+    if (a.done != nullptr && *a.done) return;
+    constexpr int NS = (MODE == WILSON_PLAIN) ? 1 : 2;
+    double acc[NS];
+#pragma unroll
+    for (int j = 0; j < NS; j++) acc[j] = 0.0;
+    const bool split_t = a.g_tp != nullptr, split_x = a.g_xp != nullptr;
+    const int ncol = split_t ? 2 * a.wx : 0;
+    const int wrow = split_x ? (split_t ? a.wt - 2 : a.wt) : 0;
+    const int total = ncol + 2 * wrow;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int x, t;
+        if (i < ncol) {
+            x = i >> 1;
+            t = (i & 1) ? a.wt - 1 : 0;
+        } else {
+            const int j = i - ncol;
+            x = (j < wrow) ? 0 : a.wx - 1;
+            t = (j < wrow ? j : j - wrow) + (split_t ? 1 : 0);
+        }
+        cplx o0, o1;
+        wilson_site<DAG>(a, x, t, o0, o1);
+        wilson_epilogue<MODE, NS>(a, x * a.wt + t, o0, o1, acc);
+    }
+    if (MODE != WILSON_PLAIN) {
+        if (grid_reduce<NS>(acc, a.partials, a.ticket, a.interior_blocks + (int)gridDim.x, a.interior_blocks + (int)blockIdx.x)) {
+            if (threadIdx.x == 0) {
                 a.sums_out[0] = acc[0];
                 a.sums_out[1] = acc[1];
             }

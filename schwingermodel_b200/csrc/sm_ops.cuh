@@ -10,7 +10,20 @@ template <bool DAG, int MODE>
 static int launch_wilson(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, double m0, const cplx* aux = nullptr,
                          cplx* r = nullptr, cplx* d = nullptr, cplx* x = nullptr, double* sums_out = nullptr,
                          const int* done = nullptr) {
-    if (c->dist()) TRY((exchange_spinor_halo<DAG>(c, U, in, done)));
+    // split lattice: pack the halo lines, exchange them on the comm stream while the interior sites compute on
+    // the compute stream, then the boundary sites on the comm stream (SM_OVERLAP=0: exchange first, one launch)
+    const bool overlap = c->dist() && c->overlap && c->wx >= 4 && c->wt >= 4;
+    if (c->dist()) {
+        if (overlap) {
+            TRY((pack_spinor_halo<DAG>(c, U, in, done)));
+            CU(cudaEventRecord(c->ev_ready, c->stream));
+            CU(cudaStreamWaitEvent(c->comm_stream, c->ev_ready, 0));
+            TRY(exchange_spinor_lines(c, c->comm_stream));
+        } else {
+            TRY((pack_spinor_halo<DAG>(c, U, in, done)));
+            TRY(exchange_spinor_lines(c, c->stream));
+        }
+    }
     WilsonArgs a{};
     a.U = U;
     a.in = in;
@@ -34,9 +47,25 @@ static int launch_wilson(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, do
     a.ticket = c->tickets + TK_WILSON;
     a.sums_out = sums_out;
     a.done = done;
-    k_wilson<DAG, MODE><<<(MODE == WILSON_PLAIN) ? c->wil_grid_plain : c->wil_grid, c->wil_block, 0, c->stream>>>(a);
-    KCHECK();
-    c->launches++;
+    const dim3 grid = (MODE == WILSON_PLAIN) ? c->wil_grid_plain : c->wil_grid;
+    if (overlap) {
+        const int nsites = (c->rt > 1 ? 2 * c->wx : 0) + (c->rx > 1 ? 2 * (c->rt > 1 ? c->wt - 2 : c->wt) : 0);
+        const int bblocks = std::max(1, std::min(64, (nsites + kBlock - 1) / kBlock));
+        a.interior_blocks = (int)(grid.x * grid.y);
+        a.boundary_blocks = bblocks;
+        k_wilson_boundary<DAG, MODE><<<bblocks, kBlock, 0, c->comm_stream>>>(a);
+        KCHECK();
+        CU(cudaEventRecord(c->ev_ghost, c->comm_stream));
+        a.interior_only = 1;
+        k_wilson<DAG, MODE><<<grid, c->wil_block, 0, c->stream>>>(a);
+        KCHECK();
+        CU(cudaStreamWaitEvent(c->stream, c->ev_ghost, 0));
+        c->launches += 2;
+    } else {
+        k_wilson<DAG, MODE><<<grid, c->wil_block, 0, c->stream>>>(a);
+        KCHECK();
+        c->launches++;
+    }
     return SM_OK;
 }
 

@@ -404,6 +404,33 @@ def test_cg_execution_strategies_agree(sb):
             assert relerr(xm, xref) <= 1e-10, name
 
 
+@pytest.mark.parametrize("nx,nt,m0", [(288, 288, 0.0), (300, 333, -0.03), (400, 401, 0.05), (512, 512, -0.1), (1100, 275, 0.0)])
+def test_grid_resident_cg_several_sites_per_thread(sb, nx, nt, m0):
+    """Lattices between one and four sites per thread of a full cooperative grid (k_cg_coop_multi, 2 / 2 / 3 / 4 / 4
+    slots on 148 SMs; ragged sizes leave empty slots; 512 x 512 is BASELINE configs[4]'s lattice): same iterate as
+    the oracle and as the CUDA-graph path, also when stopped mid-way."""
+    from oracle.port import Port, gaussian_fields
+    P = Port(nx, nt)
+    U = P.hot_start(8)
+    phi, _ = gaussian_fields(nx, nt, 9)
+    xo, oko, apps, _ = P.cg(U, phi, m0)
+    xref = P.cg(U, phi, m0, 1e-10, 7)[0]
+    for name, env in [("resident", {}), ("graphs", {"SM_COOP_SLOTS": "1"})]:
+        os.environ.update(env)
+        lat = sb.Lattice(nx, nt)
+        for k in env:
+            os.environ.pop(k)
+        x, ok, its = lat.conjugate_gradient(U, phi, m0)
+        assert ok == oko == 1 and abs(its + 2 - apps) <= 1, (name, its, apps)
+        assert relerr(x, xo) <= TOL_X, name
+        res = np.linalg.norm(phi - lat.D_D_dagger_phi(U, x, m0)) / np.linalg.norm(phi)
+        assert res <= 2e-10, (name, res)
+        lat.set_cg(1e-10, 7)
+        xm, okm, itm = lat.conjugate_gradient(U, phi, m0)
+        assert okm == 0 and itm == 7 and relerr(xm, xref) <= 1e-10, name
+        lat.close()
+
+
 def test_config2_trajectory_256_vs_oracle(sb):
     """A full trajectory at BASELINE config 2's size (grid-resident CG path): dH against the oracle."""
     from oracle.port import Port, gaussian_fields
