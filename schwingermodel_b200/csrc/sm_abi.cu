@@ -156,6 +156,8 @@ int sm_destroy(sm_ctx* c) {
     for (void* p : {(void*)c->mx_U, (void*)c->mx_r, (void*)c->mx_e, (void*)c->mx_d0, (void*)c->mx_d1, (void*)c->mx_Ad})
         if (p) cudaFree(p);
     if (c->coop_hop) cudaFree(c->coop_hop);
+    if (c->cols_hop) cudaFree(c->cols_hop);
+    if (c->cols_wsum) cudaFree(c->cols_wsum);
     if (c->coop_wsum) cudaFree(c->coop_wsum);
     if (c->coop_bar) cudaFree(c->coop_bar);
     for (auto& g : c->cg_graphs) cudaGraphExecDestroy(g.exec);

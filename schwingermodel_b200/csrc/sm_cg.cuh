@@ -2,6 +2,7 @@
 // Part of the single translation unit sm_abi.cu (static functions, included in dependency order).
 #pragma once
 #include "sm_ops.cuh"
+#include "sm_column_cg.cuh"
 
 // conjugate_gradient (src/conjugate_gradient.cpp:4-67) entirely on the device.  The host only
 // enqueues batches of iterations and polls a pinned copy of the CG scalars one batch behind, so
@@ -315,8 +316,8 @@ static int dev_cg_coop(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, doubl
     if (!c->coop_hop) {
         TRY(dev_alloc(&c->coop_hop, (size_t)8 * c->V));
         TRY(dev_alloc(&c->coop_wsum, (size_t)4 * blocks * (kCoopThreads / 32)));
-        TRY(dev_alloc(&c->coop_bar, (size_t)32));
     }
+    if (!c->coop_bar) TRY(dev_alloc(&c->coop_bar, (size_t)32));
     CU(cudaMemsetAsync(c->coop_bar, 0, sizeof(unsigned int) * 32, c->stream));
     a.hop = c->coop_hop;
     a.wsum = c->coop_wsum;
@@ -327,67 +328,90 @@ static int dev_cg_coop(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, doubl
     return resident_finish(c, converged, iterations);
 }
 
-// several sites per thread on the same cooperative grid (k_cg_coop_multi): the smallest slot count whose full grid
-// holds the lattice, 0 if none does
-template <int S>
-static int coop_multi_blocks_per_sm(sm_ctx* c) {
-    const size_t smem = coop_multi_smem(S);
-    if (cudaFuncSetAttribute(k_cg_coop_multi<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-        cudaGetLastError();
-        return 0;
-    }
+// Lattices beyond one site per thread of a full cooperative grid: k_cg_cols, S rows per thread in CTAs of T threads
+// (sm_column_cg.cuh).  The variants compiled: T = 512 with S = 1..4, T = 256 with S = 2..8.
+struct ColsVariant {
+    int S, T;
+    const void* kernel;
+};
+static const ColsVariant kColsVariants[] = {
+    {1, 512, (const void*)k_cg_cols<1, 512>}, {2, 512, (const void*)k_cg_cols<2, 512>},
+    {3, 512, (const void*)k_cg_cols<3, 512>}, {4, 512, (const void*)k_cg_cols<4, 512>},
+    {2, 256, (const void*)k_cg_cols<2, 256>}, {3, 256, (const void*)k_cg_cols<3, 256>},
+    {4, 256, (const void*)k_cg_cols<4, 256>}, {5, 256, (const void*)k_cg_cols<5, 256>},
+    {6, 256, (const void*)k_cg_cols<6, 256>}, {7, 256, (const void*)k_cg_cols<7, 256>},
+    {8, 256, (const void*)k_cg_cols<8, 256>},
+};
+
+static long long cols_blocks(const sm_ctx* c, int S, int T) {
+    const long long threads = (long long)((c->wx + S - 1) / S) * c->wt;
+    return (threads + T - 1) / T;
+}
+
+// does the variant hold this lattice on one co-resident grid?
+static bool cols_fits(sm_ctx* c, const ColsVariant& v) {
+    const size_t smem = cols_smem_bytes(v.S, v.T);
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_coop_multi<S>, kCoopThreads, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(v.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, v.kernel, v.T, smem) != cudaSuccess) {
         cudaGetLastError();
-        return 0;
+        return false;
     }
-    return per_sm;
+    return per_sm > 0 && cols_blocks(c, v.S, v.T) <= (long long)per_sm * c->sm_count;
 }
 
-static int coop_multi_slots(sm_ctx* c) {
-    if (c->coop_slots < 0) {
-        c->coop_slots = 0;
-        int coop = 0;
-        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
-        const int per_sm[kCoopMaxSlots + 1] = {0, 0, coop ? coop_multi_blocks_per_sm<2>(c) : 0,
-                                               coop ? coop_multi_blocks_per_sm<3>(c) : 0,
-                                               coop ? coop_multi_blocks_per_sm<4>(c) : 0};
-        for (int s = 2; s <= std::min(kCoopMaxSlots, c->coop_max_slots); s++) {
-            const long long blocks = ((long long)c->V + (long long)s * kCoopThreads - 1) / ((long long)s * kCoopThreads);
-            if (per_sm[s] > 0 && blocks <= (long long)per_sm[s] * c->sm_count) {
-                c->coop_slots = s;
-                break;
-            }
-        }
+// picks c->cols (variant index, -1: none) once per context.  SM_COLS=S,T forces a variant wherever it fits (also on
+// lattices the one-site kernels would take); SM_COLS=0 disables the kernel.
+static int cols_plan(sm_ctx* c) {
+    if (c->cols_planned) return c->cols;
+    c->cols_planned = true;
+    c->cols = -1;
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
+    // one tile only (the antiperiodic sign is folded into the links once), warps of >= 32 columns with <= 1 row wrap
+    if (!coop || c->dist() || c->wt < 32 || c->sR_edge() != c->sL_edge() || !c->cols_enabled) return c->cols;
+    const int nvar = (int)(sizeof(kColsVariants) / sizeof(kColsVariants[0]));
+    if (c->cols_force_S > 0) {
+        for (int i = 0; i < nvar; i++)
+            if (kColsVariants[i].S == c->cols_force_S && kColsVariants[i].T == c->cols_force_T && cols_fits(c, kColsVariants[i]))
+                c->cols = i;
+        return c->cols;
     }
-    return c->coop_slots;
+    if (c->V <= kClusterMaxCtas * kClusterThreads) return c->cols;     // one cluster holds it: k_cg_cluster
+    // fewest rows per thread that fit, 256-thread CTAs first (255 registers per thread: no spills).  Measured
+    // (profiles/r01_sweep_column_cg.txt): 256^2 9.2 us per iteration with 2 x 256 against 10.3 us with one site per
+    // thread (k_cg_coop), 128^2 equal; 384^2 11.2 us (4 x 256) and 512^2 14.6 us (8 x 256) against 25.9 / 29.6 us with
+    // CUDA graphs of the one-pass kernels.
+    for (int T : {256, 512})
+        for (int i = 0; i < nvar && c->cols < 0; i++)
+            if (kColsVariants[i].T == T && cols_fits(c, kColsVariants[i])) c->cols = i;
+    return c->cols;
 }
 
-static int dev_cg_coop_multi(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, int* converged, int* iterations) {
+static int dev_cg_cols(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, int* converged, int* iterations) {
     ResidentCgArgs a;
     TRY(resident_args(c, U, phi, x, m0, &a));
-    const int S = c->coop_slots;
-    const int blocks = (c->V + S * kCoopThreads - 1) / (S * kCoopThreads);
-    if (!c->coop_hop) {
-        TRY(dev_alloc(&c->coop_hop, (size_t)8 * c->V));
-        TRY(dev_alloc(&c->coop_wsum, (size_t)4 * ((c->V + kCoopThreads - 1) / kCoopThreads) * (kCoopThreads / 32)));
-        TRY(dev_alloc(&c->coop_bar, (size_t)32));
+    const ColsVariant& v = kColsVariants[c->cols];
+    const int blocks = (int)cols_blocks(c, v.S, v.T);
+    if (!c->cols_hop) {
+        TRY(dev_alloc(&c->cols_hop, (size_t)kColsBuffers * 4 * c->V));
+        TRY(dev_alloc(&c->cols_wsum, (size_t)4 * (c->sm_count + 32)));
     }
+    if (!c->coop_bar) TRY(dev_alloc(&c->coop_bar, (size_t)32));
     CU(cudaMemsetAsync(c->coop_bar, 0, sizeof(unsigned int) * 32, c->stream));
-    a.hop = c->coop_hop;
-    a.wsum = c->coop_wsum;
+    a.hop = c->cols_hop;
+    a.wsum = c->cols_wsum;
     a.bar = c->coop_bar;
     void* params[] = {&a};
-    const void* fn = S == 2 ? (const void*)k_cg_coop_multi<2> : S == 3 ? (const void*)k_cg_coop_multi<3> : (const void*)k_cg_coop_multi<4>;
-    CU(cudaLaunchCooperativeKernel(fn, dim3(blocks, 1, 1), dim3(kCoopThreads, 1, 1), params, coop_multi_smem(S), c->stream));
+    CU(cudaLaunchCooperativeKernel(v.kernel, dim3(blocks, 1, 1), dim3(v.T, 1, 1), params, cols_smem_bytes(v.S, v.T), c->stream));
     return resident_finish(c, converged, iterations);
 }
 
 static int dev_cg(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, int* converged, int* iterations) {
     if (c->use_cluster && !c->dist()) {
+        if (cols_plan(c) >= 0) return dev_cg_cols(c, U, phi, x, m0, converged, iterations);
         if (c->V <= kClusterMaxCtas * kClusterThreads) return dev_cg_cluster(c, U, phi, x, m0, converged, iterations);
-        if (c->V <= coop_capacity(c)) return dev_cg_coop(c, U, phi, x, m0, converged, iterations);
-        if (coop_multi_slots(c) > 0) return dev_cg_coop_multi(c, U, phi, x, m0, converged, iterations);
+        if (c->V <= coop_capacity(c)) return dev_cg_coop(c, U, phi, x, m0, converged, iterations);   // width_t < 32 or SM_COLS=0
     }
     if (c->solver == SM_SOLVER_MIXED && fused_ok(c) && !c->dist()) return dev_cg_mixed(c, U, phi, x, m0, converged, iterations);
     if (fused_ok(c)) return dev_cg_fused(c, U, phi, x, m0, converged, iterations);

@@ -42,7 +42,7 @@ struct ResidentCgArgs {
     int max_iter;
     CgState* st;
     // GridComm only
-    cplx* hop;          // [2 buffers][4 kinds][V]
+    cplx* hop;          // [buffer][4 kinds][V]: 2 buffers (k_cg_coop), 4 (k_cg_cols)
     double* wsum;       // [2 slots][2 values][blocks * warps]
     unsigned int* bar;  // monotonic arrival counter of the grid barrier (zeroed before the launch)
 };
@@ -120,42 +120,30 @@ struct ClusterComm {
 };
 
 // ---- transport 2: cooperative grid, L2-resident global buffers ----------------------------------
-struct GridComm {
-    static constexpr int kThreads = kCoopThreads;
-    static constexpr bool kXInRegisters = false;     // 128-register budget: x is updated in place in L2
-    cplx* hop;
+// barrier and sums of a cooperative grid of THREADS-thread CTAs (one per SM)
+template <int THREADS>
+struct GridSync {
     double* wsum;
     unsigned int* bar;
     unsigned int target;                             // arrivals expected at the next barrier
-    int V, n;
-    int m_tp, m_tm, m_xp, m_xm;
 
-    __device__ GridComm(const ResidentCgArgs& a)
-        : hop(a.hop), wsum(a.wsum), bar(a.bar), target(0), V(a.V),
-          n((int)blockIdx.x * kThreads + (int)threadIdx.x) {}
-    __device__ int site() const { return n; }
-    __device__ void bind(int tp, int tm, int xp, int xm) { m_tp = tp; m_tm = tm; m_xp = xp; m_xm = xm; }
-    __device__ void put(int buf, int kind, cplx v) {
-        if (n < V) __stcg(&hop[(size_t)(buf * 4 + kind) * V + n], v);
-    }
-    __device__ cplx get_tp(int buf) const { return __ldcg(&hop[(size_t)(buf * 4 + 0) * V + m_tp]); }
-    __device__ cplx get_tm(int buf) const { return __ldcg(&hop[(size_t)(buf * 4 + 1) * V + m_tm]); }
-    __device__ cplx get_xp(int buf) const { return __ldcg(&hop[(size_t)(buf * 4 + 2) * V + m_xp]); }
-    __device__ cplx get_xm(int buf) const { return __ldcg(&hop[(size_t)(buf * 4 + 3) * V + m_xm]); }
-    // Grid barrier on one monotonic counter: thread 0 of every CTA arrives with a release and spins
-    // with acquire loads until all CTAs of this round have arrived (the cooperative launch
-    // guarantees they are co-resident).  About 3x cheaper than cooperative_groups' grid.sync here.
+    __device__ GridSync(double* wsum_, unsigned int* bar_) : wsum(wsum_), bar(bar_), target(0) {}
+    // Grid barrier on one monotonic counter: thread 0 of every CTA arrives with a release and spins with acquire
+    // loads until all CTAs of this round have arrived (the cooperative launch guarantees they are co-resident).
+    // The release / acquire pair orders the whole CTA's traffic: the block barriers put every thread's stores
+    // before thread 0's release and every thread's later loads after its acquire (causality order is transitive
+    // across bar.sync), so no separate __threadfence is needed -- tools/barrier_bench.cu: 1.27 us against 1.55 us
+    // with explicit fences and 1.24 us for cooperative_groups' grid.sync (148 CTAs), 2.3 / 2.7 / 2.6 us with the
+    // half-spinor stores before and loads after.
     __device__ void barrier() {
         __syncthreads();
         if (threadIdx.x == 0) {
             target += gridDim.x;
             unsigned int seen;
-            __threadfence();   // the CTA's stores (ordered before this point by the block barrier) go out first
             asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
             do {
                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
             } while (seen < target);
-            __threadfence();
         }
         __syncthreads();
     }
@@ -164,9 +152,9 @@ struct GridComm {
     // partials with independent loads, in a fixed order
     template <int NV>
     __device__ void sum_begin(int slot, double (&v)[NV]) {
-        __shared__ double wpart[2][kThreads / 32];
+        __shared__ double wpart[2][THREADS / 32];
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        constexpr int W = kThreads / 32;
+        constexpr int W = THREADS / 32;
         const int nb = (int)gridDim.x;
 #pragma unroll
         for (int j = 0; j < NV; j++) {
@@ -205,6 +193,26 @@ struct GridComm {
         barrier();
         sum_end<NV>(slot, v);
     }
+};
+
+struct GridComm : GridSync<kCoopThreads> {
+    static constexpr int kThreads = kCoopThreads;
+    static constexpr bool kXInRegisters = false;     // 128-register budget: x is updated in place in L2
+    cplx* hop;
+    int V, n;
+    int m_tp, m_tm, m_xp, m_xm;
+
+    __device__ GridComm(const ResidentCgArgs& a)
+        : GridSync<kCoopThreads>(a.wsum, a.bar), hop(a.hop), V(a.V), n((int)blockIdx.x * kThreads + (int)threadIdx.x) {}
+    __device__ int site() const { return n; }
+    __device__ void bind(int tp, int tm, int xp, int xm) { m_tp = tp; m_tm = tm; m_xp = xp; m_xm = xm; }
+    __device__ void put(int buf, int kind, cplx v) {
+        if (n < V) __stcg(&hop[(size_t)(buf * 4 + kind) * V + n], v);
+    }
+    __device__ cplx get_tp(int buf) const { return __ldcg(&hop[(size_t)(buf * 4 + 0) * V + m_tp]); }
+    __device__ cplx get_tm(int buf) const { return __ldcg(&hop[(size_t)(buf * 4 + 1) * V + m_tm]); }
+    __device__ cplx get_xp(int buf) const { return __ldcg(&hop[(size_t)(buf * 4 + 2) * V + m_xp]); }
+    __device__ cplx get_xm(int buf) const { return __ldcg(&hop[(size_t)(buf * 4 + 3) * V + m_xm]); }
 };
 
 // ---- the solve ------------------------------------------------------------------------------------
@@ -371,197 +379,6 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_cg_cluster(const Residen
 __global__ void __launch_bounds__(kCoopThreads, 1) k_cg_coop(const ResidentCgArgs a) {
     GridComm comm(a);
     resident_cg(a, comm);
-}
-
-// ---- several sites per thread -----------------------------------------------------------------------
-// The same solve for lattices beyond one site per thread of a full grid (up to S x 512 x SMs sites, S <= 4:
-// 512 x 512, BASELINE configs[4], takes S = 4 on 148 SMs).  A thread owns the sites n0 + j 512 (j < S) of its
-// CTA's contiguous range.  What a site needs for the whole solve is split between the two on-chip stores:
-// d and the vector that crosses a barrier (t = D^dagger d, then A d, then the new r) in REGISTERS; r, x and
-// the site's two links in SHARED MEMORY (each thread touches only its own slots, 16-byte accesses at
-// consecutive addresses across a warp, so it is a conflict-free register extension of 96 B per site).
-// Half-spinors travel through the L2-resident buffers of GridComm and the barrier and sums are GridComm's.
-// Four barriers per iteration (keeping the neighbours' halves of d as the one-site kernel does would cost
-// another 64 B per site of on-chip state): t halves | dot(d, A d) | |r|^2 | d halves.
-constexpr int kCoopMaxSlots = 4;
-constexpr size_t coop_multi_smem(int slots) { return sizeof(cplx) * 3 * 2 * (size_t)slots * kCoopThreads; }
-
-template <int S>
-__global__ void __launch_bounds__(kCoopThreads, 1) k_cg_coop_multi(const ResidentCgArgs a) {
-    extern __shared__ double2 coop_smem[];
-    constexpr int T = kCoopThreads;
-    cplx* const sr = coop_smem;          // r      [component][slot][thread]
-    cplx* const su = sr + 2 * S * T;     // links  [mu][slot][thread]
-    cplx* const sx = su + 2 * S * T;     // x      [component][slot][thread]
-    GridComm comm(a);                    // barrier and sums only; the half-spinor traffic is addressed per slot
-    const int tid = threadIdx.x, V = a.V, wt = a.wt;
-    const int n0 = (int)blockIdx.x * (S * T) + tid;
-    const size_t Vs = (size_t)V;
-    cplx* const hop = a.hop;
-    const cplx zero = make_double2(0.0, 0.0);
-
-    int tcol[S];                         // t of the slot's site; -1: the slot holds no site
-#pragma unroll
-    for (int j = 0; j < S; j++) {
-        const int n = n0 + j * T;
-        tcol[j] = (n < V) ? n % wt : -1;
-    }
-
-    // the four half-spinors a site publishes for a stencil application (see resident_cg)
-    auto publish = [&](auto hop_tag, int buf, int j, cplx p0, cplx p1) {
-        using H = decltype(hop_tag);
-        if (tcol[j] < 0) return;
-        const cplx u0 = su[(0 * S + j) * T + tid], u1 = su[(1 * S + j) * T + tid];
-        cplx* h = hop + (size_t)(buf * 4) * Vs + (n0 + j * T);
-        __stcg(h, H::from_tp(p0, p1));
-        __stcg(h + Vs, cmulc(u0, H::from_tm(p0, p1)));
-        __stcg(h + 2 * Vs, H::from_xp(p0, p1));
-        __stcg(h + 3 * Vs, cmulc(u1, H::from_xm(p0, p1)));
-    };
-    // out = (m0 + 2) p - 1/2 (the four hop terms of the halves the neighbours published in `buf`)
-    auto stencil = [&](auto hop_tag, int buf, int j, cplx p0, cplx p1, cplx& o0, cplx& o1) {
-        using H = decltype(hop_tag);
-        const int t = tcol[j];
-        if (t < 0) {
-            o0 = o1 = zero;
-            return;
-        }
-        const int n = n0 + j * T;
-        const int m_tp = nb_tp(n, t, wt), m_tm = nb_tm(n, t, wt);
-        int m_xp = n + wt, m_xm = n - wt;          // rows wrap by the lattice volume
-        if (m_xp >= V) m_xp -= V;
-        if (m_xm < 0) m_xm += V;
-        const cplx* h = hop + (size_t)(buf * 4) * Vs;
-        const cplx h_tp = __ldcg(h + m_tp), h_tm = __ldcg(h + Vs + m_tm);
-        const cplx h_xp = __ldcg(h + 2 * Vs + m_xp), h_xm = __ldcg(h + 3 * Vs + m_xm);
-        const cplx u0 = su[(0 * S + j) * T + tid], u1 = su[(1 * S + j) * T + tid];
-        const double sR = (t == wt - 1) ? a.sR_edge : 1.0, sL = (t == 0) ? a.sL_edge : 1.0;
-        cplx a0, a1;
-        H::add_tp(cscale(sR, cmul(u0, h_tp)), a0, a1);
-        H::add_xp(cmul(u1, h_xp), a0, a1);
-        H::add_tm(cscale(sL, h_tm), a0, a1);
-        H::add_xm(h_xm, a0, a1);
-        o0 = make_double2(a.mass * p0.x - 0.5 * a0.x, a.mass * p0.y - 0.5 * a0.y);
-        o1 = make_double2(a.mass * p1.x - 0.5 * a1.x, a.mass * p1.y - 0.5 * a1.y);
-    };
-
-    cplx d0[S], d1[S], w0[S], w1[S];     // direction; the vector that crosses the next barrier
-
-    // x = phi ; r = phi - D D^dagger phi ; d = r   (conjugate_gradient.cpp:16-24)
-#pragma unroll
-    for (int j = 0; j < S; j++) {
-        const int n = n0 + j * T;
-        cplx f0 = zero, f1 = zero;
-        if (tcol[j] >= 0) {
-            su[(0 * S + j) * T + tid] = a.U[n];
-            su[(1 * S + j) * T + tid] = a.U[Vs + n];
-            f0 = a.phi[n];
-            f1 = a.phi[Vs + n];
-        }
-        sx[(0 * S + j) * T + tid] = f0;
-        sx[(1 * S + j) * T + tid] = f1;
-        w0[j] = f0;
-        w1[j] = f1;
-        publish(Hop<true>{}, 0, j, f0, f1);
-    }
-    comm.barrier();
-#pragma unroll
-    for (int j = 0; j < S; j++) {
-        cplx t0, t1;
-        stencil(Hop<true>{}, 0, j, w0[j], w1[j], t0, t1);
-        w0[j] = t0;
-        w1[j] = t1;
-        publish(Hop<false>{}, 1, j, t0, t1);
-    }
-    comm.barrier();
-    double s2[2] = {0.0, 0.0};
-#pragma unroll
-    for (int j = 0; j < S; j++) {
-        cplx A0, A1;
-        stencil(Hop<false>{}, 1, j, w0[j], w1[j], A0, A1);
-        const cplx f0 = sx[(0 * S + j) * T + tid], f1 = sx[(1 * S + j) * T + tid];
-        const cplx r0 = csub(f0, A0), r1 = csub(f1, A1);    // zero in an empty slot
-        sr[(0 * S + j) * T + tid] = r0;
-        sr[(1 * S + j) * T + tid] = r1;
-        d0[j] = r0;
-        d1[j] = r1;
-        s2[0] += f0.x * f0.x + f0.y * f0.y + f1.x * f1.x + f1.y * f1.y;
-        s2[1] += r0.x * r0.x + r0.y * r0.y + r1.x * r1.x + r1.y * r1.y;
-        publish(Hop<true>{}, 0, j, r0, r1);
-    }
-    comm.template sum<2>(1, s2);          // its barrier also completes the exchange of the halves of d_0
-    const double phi_norm = sqrt(s2[0]);
-    double rr = s2[1];
-
-    int k = 0, converged = 0;
-    while (k < a.max_iter) {
-#pragma unroll
-        for (int j = 0; j < S; j++) {     // t = D^dagger d
-            cplx t0, t1;
-            stencil(Hop<true>{}, 0, j, d0[j], d1[j], t0, t1);
-            w0[j] = t0;
-            w1[j] = t1;
-            publish(Hop<false>{}, 1, j, t0, t1);
-        }
-        comm.barrier();
-        double dAd[2] = {0.0, 0.0};
-#pragma unroll
-        for (int j = 0; j < S; j++) {     // Ad = D t ; alpha = r_norm2 / dot(d, Ad)   (:32-33)
-            cplx A0, A1;
-            stencil(Hop<false>{}, 1, j, w0[j], w1[j], A0, A1);
-            w0[j] = A0;
-            w1[j] = A1;
-            const cplx q0 = cmul_conj(d0[j], A0), q1 = cmul_conj(d1[j], A1);
-            dAd[0] += q0.x + q1.x;
-            dAd[1] += q0.y + q1.y;
-        }
-        comm.template sum<2>(0, dAd);
-        const cplx alpha = cdiv(make_double2(rr, 0.0), make_double2(dAd[0], dAd[1]));
-        double e2[1] = {0.0};
-#pragma unroll
-        for (int j = 0; j < S; j++) {     // x += alpha d ; r -= alpha Ad   (:34-41)
-            const int i0 = (0 * S + j) * T + tid, i1 = (1 * S + j) * T + tid;
-            sx[i0] = cadd(sx[i0], cmul(alpha, d0[j]));
-            sx[i1] = cadd(sx[i1], cmul(alpha, d1[j]));
-            const cplx r0 = csub(sr[i0], cmul(alpha, w0[j])), r1 = csub(sr[i1], cmul(alpha, w1[j]));
-            sr[i0] = r0;
-            sr[i1] = r1;
-            w0[j] = r0;
-            w1[j] = r1;
-            e2[0] += r0.x * r0.x + r0.y * r0.y + r1.x * r1.x + r1.y * r1.y;
-        }
-        comm.template sum<1>(1, e2);
-        if (sqrt(e2[0]) < a.tol * phi_norm) {   // :45
-            converged = 1;
-            break;
-        }
-        const double beta = e2[0] / rr;         // :51-59
-#pragma unroll
-        for (int j = 0; j < S; j++) {
-            d0[j] = make_double2(d0[j].x * beta + w0[j].x, d0[j].y * beta + w0[j].y);
-            d1[j] = make_double2(d1[j].x * beta + w1[j].x, d1[j].y * beta + w1[j].y);
-            publish(Hop<true>{}, 0, j, d0[j], d1[j]);
-        }
-        comm.barrier();
-        rr = e2[0];
-        k++;
-    }
-
-#pragma unroll
-    for (int j = 0; j < S; j++) {
-        if (tcol[j] >= 0) {
-            const int n = n0 + j * T;
-            a.x[n] = sx[(0 * S + j) * T + tid];
-            a.x[Vs + n] = sx[(1 * S + j) * T + tid];
-        }
-    }
-    if (n0 == 0) {
-        a.st->phi_norm2 = s2[0];
-        a.st->rr[0] = rr;
-        a.st->iters = k;
-        a.st->converged = converged;
-        a.st->done = 1;
-    }
 }
 
 }  // namespace sm

@@ -183,8 +183,11 @@ struct sm_ctx {
     cplxf *mx_U = nullptr, *mx_r = nullptr, *mx_e = nullptr, *mx_d0 = nullptr, *mx_d1 = nullptr, *mx_Ad = nullptr;
     bool use_cluster = true;   // whole-solve resident kernels for small lattices (SM_CLUSTER_CG=0 disables)
     int coop_sites = -1;
-    int coop_slots = -1;       // sites per thread of k_cg_coop_multi on this lattice (0: does not fit)
-    int coop_max_slots = 4;    // SM_COOP_SLOTS caps it (1 keeps lattices beyond one site per thread on the graph path)
+    // several rows per thread (k_cg_cols): variant chosen once per context (cols_plan)
+    bool cols_planned = false, cols_enabled = true;
+    int cols = -1, cols_force_S = 0, cols_force_T = 0;
+    cplx* cols_hop = nullptr;
+    double* cols_wsum = nullptr;
     cplx* coop_hop = nullptr;
     double* coop_wsum = nullptr;
     unsigned int* coop_bar = nullptr;
@@ -236,7 +239,15 @@ static int ctx_common_init(sm_ctx* c) {
     if (const char* e = getenv("SM_OVERLAP")) c->overlap = atoi(e) != 0;
     if (const char* e = getenv("SM_GRAPHS")) c->use_graphs = atoi(e) != 0;
     if (const char* e = getenv("SM_CLUSTER_CG")) c->use_cluster = atoi(e) != 0;
-    if (const char* e = getenv("SM_COOP_SLOTS")) c->coop_max_slots = atoi(e);
+    if (const char* e = getenv("SM_COLS")) {      // "0": off; "S,T": force a variant
+        int S = 0, T = 512;
+        const int got = sscanf(e, "%d%*[,x]%d", &S, &T);
+        c->cols_enabled = got >= 1 && S > 0;
+        if (c->cols_enabled) {
+            c->cols_force_S = S;
+            c->cols_force_T = T;
+        }
+    }
     CU(cudaEventCreate(&c->ev_a));
     CU(cudaEventCreate(&c->ev_b));
     CU(cudaEventCreateWithFlags(&c->ev_poll[0], cudaEventDisableTiming));

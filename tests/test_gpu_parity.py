@@ -406,16 +406,16 @@ def test_cg_execution_strategies_agree(sb):
 
 @pytest.mark.parametrize("nx,nt,m0", [(288, 288, 0.0), (300, 333, -0.03), (400, 401, 0.05), (512, 512, -0.1), (1100, 275, 0.0)])
 def test_grid_resident_cg_several_sites_per_thread(sb, nx, nt, m0):
-    """Lattices between one and four sites per thread of a full cooperative grid (k_cg_coop_multi, 2 / 2 / 3 / 4 / 4
-    slots on 148 SMs; ragged sizes leave empty slots; 512 x 512 is BASELINE configs[4]'s lattice): same iterate as
-    the oracle and as the CUDA-graph path, also when stopped mid-way."""
+    """Lattices beyond one site per thread of a full cooperative grid (k_cg_cols: column segments of up to 8 rows per
+    thread; ragged sizes leave empty slots; 512 x 512 is BASELINE configs[4]'s lattice): same iterate as the oracle and
+    as the CUDA-graph path, also when stopped mid-way."""
     from oracle.port import Port, gaussian_fields
     P = Port(nx, nt)
     U = P.hot_start(8)
     phi, _ = gaussian_fields(nx, nt, 9)
     xo, oko, apps, _ = P.cg(U, phi, m0)
     xref = P.cg(U, phi, m0, 1e-10, 7)[0]
-    for name, env in [("resident", {}), ("graphs", {"SM_COOP_SLOTS": "1"})]:
+    for name, env in [("columns", {}), ("columns 4x512", {"SM_COLS": "4,512"}), ("graphs", {"SM_COLS": "0"})]:
         os.environ.update(env)
         lat = sb.Lattice(nx, nt)
         for k in env:
@@ -428,6 +428,31 @@ def test_grid_resident_cg_several_sites_per_thread(sb, nx, nt, m0):
         lat.set_cg(1e-10, 7)
         xm, okm, itm = lat.conjugate_gradient(U, phi, m0)
         assert okm == 0 and itm == 7 and relerr(xm, xref) <= 1e-10, name
+        lat.close()
+
+
+@pytest.mark.parametrize("nx,nt,m0", [(96, 100, 0.02), (70, 33, -0.05), (131, 32, 0.1), (37, 45, 0.0), (66, 64, 0.0),
+                                      (256, 256, 0.0)])
+def test_column_segment_cg_every_segment_length(sb, nx, nt, m0):
+    """k_cg_cols forced with 1 ... 8 rows per thread (512- and 256-thread CTAs) on lattices the one-site kernels would
+    take: rows that do not divide by the segment length, row wraps in the middle of a warp (width_t not a multiple of
+    32), one-row groups."""
+    from oracle.port import Port, gaussian_fields
+    P = Port(nx, nt)
+    U = P.hot_start(18)
+    phi, _ = gaussian_fields(nx, nt, 19)
+    xo, oko, apps, _ = P.cg(U, phi, m0)
+    xref = P.cg(U, phi, m0, 1e-10, 9)[0]
+    for s in ("1,512", "2,512", "3,512", "4,512", "2,256", "3,256", "5,256", "8,256"):
+        os.environ["SM_COLS"] = s
+        lat = sb.Lattice(nx, nt)
+        os.environ.pop("SM_COLS")
+        x, ok, its = lat.conjugate_gradient(U, phi, m0)
+        assert ok == oko == 1 and abs(its + 2 - apps) <= 1, (s, its, apps)
+        assert relerr(x, xo) <= TOL_X, s
+        lat.set_cg(1e-10, 9)
+        xm, okm, itm = lat.conjugate_gradient(U, phi, m0)
+        assert okm == 0 and itm == 9 and relerr(xm, xref) <= 1e-10, s
         lat.close()
 
 
