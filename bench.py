@@ -238,6 +238,10 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
 
+    if os.environ.get("SM_BENCH_TRACE"):     # debugging aid: dump every rank's Python stack after that many seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["SM_BENCH_TRACE"]), exit=True)
+
     import schwingermodel_b200 as sb
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -272,10 +276,15 @@ def run_b200(args):
 
     L = args.lattice
     weak = args.scaling == "weak"
-    Lx = L * N if weak else L          # weak: every GPU keeps an L x L tile, the lattice grows along x
-    sites = Lx * L
+    rt = args.ranks_t                  # default 1: split along x only (contiguous halo rows, one-pass D D^dagger)
+    if N % rt:
+        raise SystemExit("--ranks-t must divide the number of GPUs")
+    rx = N // rt
+    Lx = L * rx if weak else L         # weak: every GPU keeps an L x L tile
+    Lt = L * rt if weak else L
+    sites = Lx * Lt
     m0, beta = 0.0, 2.0
-    lat = sb.Lattice(Lx, L, device=local_rank, ranks_x=N, ranks_t=1, rank=rank, nccl_id=nccl_id)
+    lat = sb.Lattice(Lx, Lt, device=local_rank, ranks_x=rx, ranks_t=rt, rank=rank, nccl_id=nccl_id)
     halo = "none"
     if N > 1:
         halo = "nccl send/recv"
@@ -293,7 +302,9 @@ def run_b200(args):
         sampler.start()
     t_load = time.time()
     lat.dev_DDdag_loop(dU, dphi, dout, m0, max(args.warmup, 3))
-    while time.time() - t_load < 0.4:      # keep the GPU under this load long enough for clocks to settle
+    # keep the GPU under this load long enough for clocks to settle; every rank must make the same number of calls
+    # (each one exchanges halos with its neighbours), so the ranks agree on the elapsed time
+    while max_over_ranks(time.time() - t_load) < 0.4:
         lat.dev_DDdag_loop(dU, dphi, dout, m0, max(args.warmup, 3))
     l0 = lat.launch_count()
     barrier()
@@ -367,8 +378,8 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"DD^dagger on {Lx}x{L}, beta=2, m0=0, hot-start links, Gaussian source "
-                               f"(BASELINE configs[3]{' tile per GPU' if weak else ''}); ranks_x={N}, ranks_t=1",
+        "config": {"workload": f"DD^dagger on {Lx}x{Lt}, beta=2, m0=0, hot-start links, Gaussian source "
+                               f"(BASELINE configs[3]{' tile per GPU' if weak else ''}); ranks_x={rx}, ranks_t={rt}",
                    "l2": "inputs larger than L2 (each field %.0f MiB per GPU)" % (V * 32 / 2 ** 20),
                    "step": "one D D^dagger application over the whole lattice", "halo_exchange": halo},
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
@@ -388,7 +399,7 @@ def run_b200(args):
         dt = max_over_ranks(time.perf_counter() - t0)
         big["cg"] = {"solves_per_s": 1.0 / dt, "iterations": its, "converged": ok, "seconds": dt,
                      "GBs_per_gpu_320B": 320.0 * V * (its + 1) / dt / 1e9,
-                     "config": f"one (D D^dagger)^-1 solve on {Lx}x{L}, hot start, m0=0, tol 1e-10, device-resident"}
+                     "config": f"one (D D^dagger)^-1 solve on {Lx}x{Lt}, hot start, m0=0, tol 1e-10, device-resident"}
         if N == 1:
             # opt-in solver upgrade: same stopping criterion on the true residual, different iterate
             lat.set_solver(True)
@@ -410,7 +421,7 @@ def run_b200(args):
         dt = max_over_ranks(time.perf_counter() - t0)
         big["hmc"] = {"traj_per_s": 1.0 / dt, "seconds": dt, "dd_applications": int(r.dd_applications),
                       "cg_solves": int(r.cg_solves), "all_cg_converged": bool(r.cg_all_converged), "dH": r.dH,
-                      "config": f"one HMC trajectory on {Lx}x{L}, beta=2, m0=0, MD=10, tau=1, hot start, device-resident"}
+                      "config": f"one HMC trajectory on {Lx}x{Lt}, beta=2, m0=0, MD=10, tau=1, hot start, device-resident"}
         line["extra"] = {f"lattice_{L}": big}
         if N == 1:
             line["extra"].update(extra_metrics(sb, args))
@@ -478,6 +489,8 @@ def main():
     ap.add_argument("--ref-lattice", type=int, default=2048)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--skip-extra", action="store_true")
+    ap.add_argument("--ranks-t", type=int, default=1,
+                    help="GPUs along t (default 1: all GPUs along x); > 1 exercises the strided-halo two-pass path")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong (default): the 8192^2 lattice of configs[3] split over N GPUs; weak: an 8192^2 tile per GPU")
     args = ap.parse_args()
