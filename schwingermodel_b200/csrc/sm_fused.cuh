@@ -246,8 +246,6 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_fused(const FusedArgsT<C> a) {
         for (int s = 0; s < 6; s++) {
             const int j = jb + s;
             if (j > j_last) break;                         // uniform over the block
-            constexpr int kUnused = 0;
-            (void)kUnused;
             const int c = s % 3, m1 = (s + 2) % 3, m2 = (s + 1) % 3;   // ring slots of rows j, j-1, j-2
             const int tn_i = s % 2, t2_i = (s + 1) % 2;
 
