@@ -255,6 +255,83 @@ def test_adjointness_gamma5_linearity(sb, nx, nt):
     lat.close()
 
 
+def _cheap_fields(nx, nt, block=64):
+    """Full-size inputs in a few seconds: a random block of `block` rows repeated along x, every row turned by its own
+    random phase (so no two rows are equal and nothing is periodic in x).  Links have unit modulus, the source is
+    Gaussian."""
+    assert nx % block == 0
+    rng = np.random.default_rng(99)
+    reps = nx // block
+    turn = np.exp(2j * np.pi * rng.random(nx)).reshape(reps, block, 1)
+    fields = []
+    for gaussian in (False, True):
+        f = np.empty((2, nx * nt), np.complex128)
+        for mu in range(2):
+            if gaussian:
+                base = rng.standard_normal((block, nt)) + 1j * rng.standard_normal((block, nt))
+            else:
+                base = np.exp(2j * np.pi * rng.random((block, nt)))
+            np.multiply(base[None, :, :], turn, out=f[mu].reshape(reps, block, nt))
+        fields.append(f)
+    return fields[0], fields[1]
+
+
+def test_full_size_8192_properties(sb):
+    """BASELINE configs[3]'s lattice itself (8192 x 8192, 2 GiB per field), device-resident:
+      * the one-pass D D^dagger equals the two stencil passes everywhere (every strip and chunk boundary of the
+        temporally blocked kernel), and both equal the oracle on bands of rows -- a band of the lattice with two extra
+        rows on each side is an exact sub-problem for its interior rows (D D^dagger reaches two rows; t is kept whole,
+        so the antiperiodic seam is the lattice's own);
+      * <D a, b> = <a, D^dagger b>;
+      * the CG solution's TRUE residual meets the reference's stopping rule."""
+    import psutil
+    if psutil.virtual_memory().available < 24 * 2 ** 30:
+        pytest.skip("needs ~16 GiB of host memory")
+    from oracle.port import Port
+    n, m0 = 8192, 0.0
+    V = n * n
+    U, phi = _cheap_fields(n, n)
+    one = sb.Lattice(n, n)
+    assert one.one_pass_dd()
+    dU, dphi, dout = one.new_field(True, U), one.new_field(True, phi), one.new_field(True)
+    one.dev_DDdag(dU, dphi, dout, m0)
+    got = dout.download()
+    # two stencil passes on the same fields (dev_D never takes the one-pass kernel)
+    dtmp = one.new_field(True)
+    one.dev_D(dU, dphi, dtmp, m0, True)
+    one.dev_D(dU, dtmp, dout, m0, False)
+    two = dout.download()
+    scale = np.abs(two[:, :4 * n]).max()
+    assert np.abs(got - two).max() <= 1e-14 * scale * 10
+    del two
+    # bands against the oracle: rows [x0, x0 + R) with two extra rows on each side, wrapped in x
+    R = 60
+    for x0 in (0, 1000, 4093, n - R):
+        rows = np.arange(x0 - 2, x0 + R + 2) % n
+        idx = (rows[:, None] * n + np.arange(n)[None, :]).ravel()
+        P = Port(R + 4, n)
+        want = P.DDdag(np.ascontiguousarray(U[:, idx]), np.ascontiguousarray(phi[:, idx]), m0)
+        inner = slice(2 * n, (R + 2) * n)
+        assert relerr(got[:, idx][:, inner], want[:, inner]) <= 2 * TOL_D, x0
+    del got
+    # adjointness at full size: a = phi, b = a second field (the links serve: unit modulus, uncorrelated with phi)
+    db = dU
+    one.dev_D(dU, dphi, dtmp, m0, False)              # D a
+    lhs = one.dev_dot(dtmp, db)
+    bound = np.sqrt(one.dev_dot(dtmp, dtmp).real * one.dev_dot(db, db).real)    # |<D a, b>| <= |D a| |b|
+    one.dev_D(dU, db, dtmp, m0, True)                 # D^dagger b
+    rhs = one.dev_dot(dphi, dtmp)
+    assert abs(lhs - rhs) <= 1e-12 * bound, (lhs, rhs, bound)
+    # CG: converged flag and true residual
+    dx = dtmp
+    ok, its = one.dev_cg(dU, dphi, dx, m0)
+    assert ok == 1 and 50 < its < 400
+    one.dev_DDdag(dU, dx, dout, m0)
+    res = phi - dout.download()
+    assert np.linalg.norm(res.ravel()) <= 3e-10 * np.linalg.norm(phi.ravel())
+    one.close()
+
+
 def test_free_field_symbol(sb):
     nx, nt, m0 = 8, 12, 0.3
     lat = sb.Lattice(nx, nt)
