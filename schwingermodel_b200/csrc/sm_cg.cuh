@@ -304,7 +304,7 @@ static int coop_capacity(sm_ctx* c) {
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
         if (!coop || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_coop, kCoopThreads, 0) != cudaSuccess)
             per_sm = 0;
-        c->coop_sites = per_sm * c->sm_count * kCoopThreads;
+        c->coop_sites = std::min(per_sm * c->sm_count, kGridSyncMaxCtas) * kCoopThreads;
     }
     return c->coop_sites;
 }
@@ -357,7 +357,8 @@ static bool cols_fits(sm_ctx* c, const ColsVariant& v) {
         cudaGetLastError();
         return false;
     }
-    return per_sm > 0 && cols_blocks(c, v.S, v.T) <= (long long)per_sm * c->sm_count;
+    // GridSync::sum_end adds at most kGridSyncMaxCtas CTA partials (5 per lane)
+    return per_sm > 0 && cols_blocks(c, v.S, v.T) <= std::min<long long>((long long)per_sm * c->sm_count, kGridSyncMaxCtas);
 }
 
 // picks c->cols (variant index, -1: none) once per context.  SM_COLS=S,T forces a variant wherever it fits (also on

@@ -30,6 +30,7 @@ namespace cgx = cooperative_groups;
 constexpr int kClusterMaxCtas = 16;
 constexpr int kClusterThreads = 256;
 constexpr int kCoopThreads = 512;
+constexpr int kGridSyncMaxCtas = 160;   // CTAs whose partial sums GridSync::sum_end adds (5 per lane)
 
 struct ResidentCgArgs {
     const cplx* U;
@@ -180,6 +181,7 @@ struct GridSync {
             const double* part = wsum + (size_t)(slot * 2 + j) * nb;
             double p[5];
 #pragma unroll
+            static_assert(kGridSyncMaxCtas == 5 * 32, "five partials per lane");
             for (int i = 0; i < 5; i++) p[i] = (lane + 32 * i < nb) ? __ldcg(part + lane + 32 * i) : 0.0;
             double acc = ((p[0] + p[1]) + (p[2] + p[3])) + p[4];
 #pragma unroll
