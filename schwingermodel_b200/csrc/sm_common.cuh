@@ -67,6 +67,7 @@ __device__ __forceinline__ void st_stream(cplxf* p, cplxf v) {
 constexpr int kBlock = 256;          // threads per block for every kernel
 constexpr int kWarps = kBlock / 32;
 constexpr int kMaxSums = 4;          // doubles reduced per kernel (<= 2 complex numbers)
+constexpr int kWilsonBoundaryBlocks = 64;   // most blocks k_wilson_boundary is launched with
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -332,7 +332,8 @@ static int ctx_common_init(sm_ctx* c) {
     c->flat_blocks_c = std::max(1, std::min(cap, (2 * c->V + kBlock - 1) / kBlock));
     c->flat_blocks_s = std::max(1, std::min(cap, (c->V + kBlock - 1) / kBlock));
 
-    const size_t max_blocks = std::max<size_t>(std::max<size_t>((size_t)nT * GY, (size_t)cap),
+    // (+ kWilsonBoundaryBlocks: on a split lattice the boundary launch of a stencil pass joins its reduction)
+    const size_t max_blocks = std::max<size_t>(std::max<size_t>((size_t)nT * GY + kWilsonBoundaryBlocks, (size_t)cap),
                                                (size_t)c->fus_grid.x * (std::max<size_t>(c->fus_grid.y, c->fus_split_chunks) + 2));
     TRY(dev_alloc(&c->partials, max_blocks * kMaxSums));
     TRY(dev_alloc(&c->tickets, (size_t)TK_COUNT));

@@ -50,7 +50,7 @@ static int launch_wilson(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, do
     const dim3 grid = (MODE == WILSON_PLAIN) ? c->wil_grid_plain : c->wil_grid;
     if (overlap) {
         const int nsites = (c->rt > 1 ? 2 * c->wx : 0) + (c->rx > 1 ? 2 * (c->rt > 1 ? c->wt - 2 : c->wt) : 0);
-        const int bblocks = std::max(1, std::min(64, (nsites + kBlock - 1) / kBlock));
+        const int bblocks = std::max(1, std::min(kWilsonBoundaryBlocks, (nsites + kBlock - 1) / kBlock));
         a.interior_blocks = (int)(grid.x * grid.y);
         a.boundary_blocks = bblocks;
         k_wilson_boundary<DAG, MODE><<<bblocks, kBlock, 0, c->comm_stream>>>(a);
