@@ -164,6 +164,8 @@ SM_API int sm_hmc_set_gauge(sm_ctx* ctx, const double* h_U0, const double* h_U1)
 SM_API int sm_hmc_get_gauge(sm_ctx* ctx, double* h_U0, double* h_U1, int proposal);        /* download U (0) or U' (1) */
 SM_API int sm_hmc_get_momenta(sm_ctx* ctx, double* h_pi0, double* h_pi1, int proposal);
 SM_API int sm_hmc_get_phi(sm_ctx* ctx, double* h_phi0, double* h_phi1);
+/* the Gaussian chi of HMC::RandomCHI (hmc.cpp:19-28) as refreshed or injected (statistical tests of the generator) */
+SM_API int sm_hmc_get_chi(sm_ctx* ctx, double* h_chi0, double* h_chi1);
 /* HMC::RandomPI + HMC::RandomCHI (hmc.cpp:5-28) from a counter-based device generator */
 SM_API int sm_hmc_refresh(sm_ctx* ctx, uint64_t seed, uint64_t trajectory_index);
 /* same fields supplied by the caller (parity tests: identical pi, chi on both sides) */

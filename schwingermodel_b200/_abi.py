@@ -86,6 +86,7 @@ _SIGS = {
     "sm_hmc_get_gauge": [ctx_p, dp, dp, C.c_int],
     "sm_hmc_get_momenta": [ctx_p, dp, dp, C.c_int],
     "sm_hmc_get_phi": [ctx_p, dp, dp],
+    "sm_hmc_get_chi": [ctx_p, dp, dp],
     "sm_hmc_refresh": [ctx_p, C.c_uint64, C.c_uint64],
     "sm_hmc_inject": [ctx_p, dp, dp, dp, dp],
     "sm_hmc_trajectory": [ctx_p, C.POINTER(TrajResult)],

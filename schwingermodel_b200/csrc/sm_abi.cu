@@ -537,6 +537,14 @@ int sm_hmc_get_phi(sm_ctx* c, double* p0, double* p1) {
     return sync(c);
 }
 
+int sm_hmc_get_chi(sm_ctx* c, double* p0, double* p1) {
+    TRY(set_device(c));
+    NEED(p0); NEED(p1);
+    if (!c->hmc_ready) return fail(SM_ERR_STATE, "HMC not configured");
+    TRY(d2h_c(c, c->chi, p0, p1));
+    return sync(c);
+}
+
 int sm_hmc_refresh(sm_ctx* c, uint64_t seed, uint64_t trajectory_index) {
     TRY(set_device(c));
     TRY(hmc_alloc(c));

@@ -271,6 +271,11 @@ class Lattice:
         check(self.lib.sm_hmc_get_phi(self.ctx, _p(p[0]), _p(p[1])))
         return p
 
+    def hmc_get_chi(self):
+        p = np.empty((2, self.V), np.complex128)
+        check(self.lib.sm_hmc_get_chi(self.ctx, _p(p[0]), _p(p[1])))
+        return p
+
     def hmc_refresh(self, seed, trajectory_index):
         check(self.lib.sm_hmc_refresh(self.ctx, int(seed), int(trajectory_index)))
 

@@ -15,6 +15,28 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def _cuda_device_present():
+    """A cheap probe that needs neither torch's CUDA init nor our library: the driver's device nodes."""
+    if os.environ.get("SM_FORCE_GPU_TESTS") == "1":
+        return True
+    try:
+        import torch
+        return bool(torch.cuda.is_available())
+    except Exception:  # noqa: BLE001
+        return any(os.path.exists(f"/dev/nvidia{i}") for i in range(8))
+
+
+def pytest_collection_modifyitems(config, items):
+    """`gpu`-marked tests are skipped (not errored) on a host without a usable CUDA device, so a plain
+    `pytest tests` stays green on CPU-only CI; on the B200 box they run (and fail loudly if the library is missing)."""
+    if _cuda_device_present():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device on this host (libschwinger_b200 has no CPU fallback)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 def load_golden(nx, nt):
     return np.load(os.path.join(GOLDEN, f"ref_{nx}x{nt}.npz"))
 

@@ -21,13 +21,9 @@ def rel(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
 
 
-def main():
-    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    local = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    decomps = [(rx, world // rx) for rx in range(1, world + 1) if world % rx == 0]
-    nx, nt, m0, beta, md, tau = 64, 48, -0.05, 2.0, 5, 0.5
+def check_lattice(nx, nt, decomps, rank, world, local):
+    """Every kernel path of a split lattice against the single-rank oracle on the global nx x nt lattice."""
+    m0, beta, md, tau = -0.05, 2.0, 5, 0.5
     P = Port(nx, nt)
     U = P.hot_start(12345)
     chi, pi = gaussian_fields(nx, nt, 777)
@@ -53,6 +49,7 @@ def main():
         dist.broadcast(idt, 0)
         lat = sb.Lattice(nx, nt, device=local, ranks_x=rx, ranks_t=rt, rank=rank, nccl_id=idt.cpu().numpy().tobytes())
         os.environ.pop("SM_DD_PATH", None)
+        one_pass = lat.one_pass_dd()
         if path == "onepass+p2p":
             lat.p2p_connect_all(dist)     # halo rows by peer-memory stores instead of NCCL send/recv
         T = lambda f: tile_of(f, nx, nt, rx, rt, rank)   # noqa: E731
@@ -99,9 +96,29 @@ def main():
         tol["U'"] = 1e-9
         tol["pi'"] = 1e-8
         bad = {k: v for k, v in e.items() if not v <= tol[k]}
-        report.append({"ranks_x": rx, "ranks_t": rt, "path": path or "default", "errors": e, "bad": bad})
+        report.append({"lattice": [nx, nt], "ranks_x": rx, "ranks_t": rt, "path": path or "default",
+                       "one_pass": one_pass, "errors": e, "bad": bad})
         assert not bad, (rx, rt, bad)
         dist.barrier()
+    return report
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    all_decomps = [(rx, world // rx) for rx in range(1, world + 1) if world % rx == 0]
+    report = []
+    # 64 x 48: every decomposition.  512 x 48 split along x only: tiles of >= 64 rows at 8 ranks, so the one-pass pass is
+    # the split launch (interior chunks on the compute stream, boundary bands behind the exchange on the comm stream)
+    # at every GPU count.  48 x 512 split along t only: tiles >= 64 columns wide, the overlapped k_wilson_boundary path.
+    # 256 x 256: the 2-D decompositions at a size where every tile still has an interior.
+    lattices = [(64, 48, all_decomps), (512, 48, [(world, 1)]), (48, 512, [(1, world)])]
+    if world >= 4:
+        lattices.append((256, 256, [d for d in all_decomps if d[0] > 1 and d[1] > 1]))
+    for nx, nt, decomps in lattices:
+        report += check_lattice(nx, nt, decomps, rank, world, local)
     if rank == 0:
         print(json.dumps({"world": world, "checked": report}))
         print("DIST_CHECK_OK")

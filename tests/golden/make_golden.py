@@ -84,7 +84,44 @@ def scalars_64():
     print("64x64: cg apps", apps, "dH", tr["dH"])
 
 
+def fingerprint_sites(n, count=256, seed=8192):
+    """Sites sampled for the full-size fingerprint: seeded random ones plus the corners of the lattice, the
+    antiperiodic seam columns and the wrap rows (where the one-pass kernel's strips and chunks begin and end)."""
+    rng = np.random.default_rng(seed)
+    xs = rng.integers(0, n, count - 16)
+    ts = rng.integers(0, n, count - 16)
+    ex = np.array([0, 0, n - 1, n - 1, 1, n - 2, 0, n - 1, 2, 3, n // 2, n // 2 - 1, 251, 252, 253, 4095])
+    et = np.array([0, n - 1, 0, n - 1, 1, n - 2, n // 2, n // 2, n - 1, 0, 0, n - 1, 251, 252, 253, 4096])
+    return np.concatenate([xs, ex]) * n + np.concatenate([ts, et])
+
+
+def fingerprint_8192(ranks=8):
+    """BASELINE configs[3] at its own size, produced by the UNMODIFIED reference over `ranks` forked ranks
+    (ranks_x = ranks, ranks_t = 1; multi-rank == single-rank is pinned by tests/test_oracle_vs_reference.py):
+    hot start srand(12345), Gaussian source (seed 777), m0 = 0:  D D^dagger phi and the CG solution at 256 sites,
+    the CG's application count and norms.  ~10 minutes on 8 cores."""
+    n = 8192
+    R = Ref(n, n)
+    U = R.hot_start(12345)
+    phi, _ = gaussian_fields(n, n, 777)
+    idx = fingerprint_sites(n)
+    sec, _, dd = R.timed("dd", U, phi, 0.0, ranks, 1, reps=1, want_out=True)
+    print(f"8192^2 D D^dagger by the reference on {ranks} ranks: {sec:.2f} s", flush=True)
+    dd_s, dd_norm = dd[:, idx].copy(), float(np.linalg.norm(dd.ravel()))
+    del dd
+    sec, apps, x = R.timed("cg", U, phi, 0.0, ranks, 1, want_out=True)
+    print(f"8192^2 CG by the reference: {sec:.1f} s, {apps} applications", flush=True)
+    np.savez_compressed(os.path.join(OUT, "ref_8192x8192_fingerprint.npz"), sites=idx, m0=0.0, hot_start_seed=12345,
+                        source_seed=777, ranks_x=ranks, U_s=U[:, idx], phi_s=phi[:, idx], dd_s=dd_s, dd_norm=dd_norm,
+                        cg_apps=apps, cg_x_s=x[:, idx], cg_x_norm=float(np.linalg.norm(x.ravel())),
+                        cg_x_sum=np.array([x.sum().real, x.sum().imag]), cg_seconds=sec)
+    print("wrote ref_8192x8192_fingerprint.npz")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "8192":
+        fingerprint_8192()
+        sys.exit(0)
     for c in CASES:
         make(*c)
     scalars_64()
