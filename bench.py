@@ -389,10 +389,12 @@ def run_b200(args):
     lat = sb.Lattice(Lx, Lt, device=local_rank, ranks_x=rx, ranks_t=rt, rank=rank, nccl_id=nccl_id)
     halo = "none"
     if N > 1:
-        halo = "nccl send/recv"
-        if os.environ.get("SM_P2P", "0") == "1":     # opt-in: measured no faster than overlapped NCCL
-            lat.p2p_connect_all(dist)       # halo rows stored straight into the neighbour's HBM over NVLink
-            halo = "peer-memory stores (CUDA IPC) + stream-ordered flag waits"
+        # x-only splits map every rank's window into every other rank at creation (CUDA IPC over NVLink): halo rows
+        # are stored straight into the neighbour's HBM and the CG sums are gathered by the kernels; SM_P2P=0 or a
+        # split along t keeps ncclSend/Recv + ncclAllReduce
+        halo = {0: "nccl send/recv, sums by ncclAllReduce", 1: "peer-memory stores (CUDA IPC) + flags, sums by ncclAllReduce",
+                2: "peer-memory stores (CUDA IPC) + flags; CG sums gathered by the kernels over peer memory, "
+                   "CG batches as CUDA graphs"}[lat.peer_mode()]
     V = lat.V
     SEED_U, SEED_PHI = 1000, 2000
     U_h = synthetic_tile("links", SEED_U, Lx, Lt, rx, rt, rank)        # tiles of ONE global field: the same lattice at every N

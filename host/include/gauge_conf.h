@@ -36,7 +36,6 @@ public:
     double MeasureSp_HMC();                           // sum Re U_01 (plaquettes must be current)
     double Compute_gaugeAction(const double& beta);   // beta * sum Re(1 - U_01)
 
-    void read_conf(const std::string& name);    // text: x t mu re im per line
     void readBinary(const std::string& name);   // the .ctxt format SaveConf writes
 };
 

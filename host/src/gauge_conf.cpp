@@ -114,23 +114,3 @@ void GaugeConf::readBinary(const std::string& name) {
     }
     scatter_global(GlobalConf, Conf);
 }
-
-void GaugeConf::read_conf(const std::string& name) {
-    spinor GlobalConf(LV::Ntot);
-    int ok = 1;
-    if (mpi::rank == 0) {
-        std::ifstream in(name);
-        ok = (bool)in;
-        int x, t, mu;
-        double re, im;
-        while (ok && (in >> x >> t >> mu >> re >> im))
-            (mu == 0 ? GlobalConf.mu0 : GlobalConf.mu1)[x * LV::Nt + t] = c_double(re, im);
-        if (ok) std::cout << "Conf read from " << name << std::endl;
-    }
-    b200::bcast(&ok, sizeof(int));
-    if (!ok) {
-        if (mpi::rank == 0) std::cerr << "File " << name << " not found " << std::endl;
-        exit(1);
-    }
-    scatter_global(GlobalConf, Conf);
-}

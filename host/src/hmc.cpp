@@ -40,12 +40,14 @@ void HMC::HMC_Update() {
     dd_apps_total += r.dd_applications;
     device_ms_total += r.kernel_ms;
     CG_convergence = r.cg_all_converged;
-    if (!CG_convergence) {
-        // hmc.cpp:48-56: dump the current (accepted) configuration for inspection
+    // hmc.cpp:46-56: every Force whose CG did not converge dumps the current (accepted) configuration GConf -- not the
+    // proposal that failed -- and bumps illConfId; the two Action solves do not (their dump is commented out, :121-131).
+    // The trajectory has already run on the device, so the dumps come after it: same files, same contents.
+    for (int f = 0; f < r.cg_force_failures; f++) {
         std::ostringstream name;
         name << "2D_U1_" << Nx << "x" << Nt << "_b" << format(beta) << "_m" << format(m0) << "_illConf" << illConfId
              << ".ctxt";
-        pull_conf();
+        if (f == 0) pull_conf();
         SaveConf(GConf, name.str());
         illConfId += 1;
     }

@@ -51,9 +51,45 @@ void check(int rc, const char* what) {
     exit(1);
 }
 
+// CUDA devices visible to this process, asked from a throw-away child so that the parent reaches fork() without a
+// CUDA context (a context does not survive fork).  -1: could not ask.
+static int visible_devices() {
+    int fd[2];
+    if (pipe(fd) != 0) return -1;
+    fflush(nullptr);
+    pid_t pid = fork();
+    if (pid < 0) return -1;
+    if (pid == 0) {
+        close(fd[0]);
+        int n = 0;
+        if (sm_device_count(&n) != SM_OK) n = 0;
+        if (::write(fd[1], &n, sizeof(n)) != (ssize_t)sizeof(n)) _exit(1);
+        _exit(0);
+    }
+    close(fd[1]);
+    int n = -1;
+    if (::read(fd[0], &n, sizeof(n)) != (ssize_t)sizeof(n)) n = -1;
+    close(fd[0]);
+    int st = 0;
+    waitpid(pid, &st, 0);
+    return n;
+}
+
 void spawn_ranks(int n_ranks) {
     mpi::size = n_ranks;
     mpi::rank = 0;
+    if (n_ranks > 1) {
+        // one GPU per rank: refuse here, before any worker exists, instead of leaving the other ranks stuck in the
+        // NCCL rendezvous when one of them finds no device
+        int first = 0;
+        if (const char* d = std::getenv("SM_DEVICE")) first = std::atoi(d);
+        const int have = visible_devices();
+        if (have >= 0 && first + n_ranks > have) {
+            std::cerr << "ranks_x*ranks_t = " << n_ranks << " ranks need GPUs " << first << ".." << first + n_ranks - 1
+                      << " but only " << have << " CUDA device(s) are visible (one GPU per rank, no CPU fallback)" << std::endl;
+            exit(1);
+        }
+    }
     for (int r = 1; r < n_ranks; r++) {
         int sv[2];
         if (socketpair(AF_UNIX, SOCK_STREAM, 0, sv) != 0) {

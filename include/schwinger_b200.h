@@ -68,6 +68,14 @@ SM_API int sm_nccl_unique_id(void* out_id /* SM_NCCL_ID_BYTES */);
  * ranks' handles in rank order (MPI_Allgather in the reference's world) and every rank connects. */
 SM_API int sm_p2p_handle(sm_ctx* ctx, void* handle_out /* SM_P2P_HANDLE_BYTES */);
 SM_API int sm_p2p_connect(sm_ctx* ctx, const void* all_handles /* nranks * SM_P2P_HANDLE_BYTES, rank order */);
+/* number of CUDA devices visible to this process; initialises the CUDA runtime, so a launcher that forks one process
+   per GPU (the stand-in for `mpirun -n ranks_x*ranks_t`, README.md:49 of the reference) asks from a throw-away child */
+SM_API int sm_device_count(int* n);
+/* how this context exchanges halos and sums (the reference: MPI_Send/Recv, src/dirac_operator.cpp:66-88, and
+   MPI_Allreduce, include/variables.h:190): 0 = single tile or NCCL send/recv + all-reduce; 1 = halo rows by peer-memory
+   stores; 2 = halo rows and the CG iteration's sums by the kernels themselves over peer memory (no NCCL in the loop).
+   sm_create_dist connects the windows itself on lattices split along x (SM_P2P=0 in the environment disables). */
+SM_API int sm_peer_mode(const sm_ctx* ctx, int* mode);
 SM_API int sm_destroy(sm_ctx* ctx);
 SM_API const char* sm_last_error(void);
 /* local tile: dims[0]=width_x, dims[1]=width_t, dims[2]=rank, dims[3]=nranks */
@@ -157,6 +165,8 @@ typedef struct {
     long long dd_applications;        /* D D^dagger applications in all CG solves of the trajectory */
     int cg_solves, cg_all_converged;
     double kernel_ms;                 /* device time of the trajectory */
+    int cg_force_failures;            /* CG solves inside HMC::Force that did not converge (hmc.cpp:46-56: one illConf dump each) */
+    int reserved_;
 } sm_traj_result;
 
 SM_API int sm_hmc_configure(sm_ctx* ctx, const sm_hmc_params* p);

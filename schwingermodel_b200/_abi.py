@@ -34,7 +34,7 @@ class TrajResult(C.Structure):
         ("sum_re_plaq_new", C.c_double), ("gauge_action_new", C.c_double),
         ("sum_re_plaq_old", C.c_double), ("gauge_action_old", C.c_double),
         ("dd_applications", C.c_longlong), ("cg_solves", C.c_int), ("cg_all_converged", C.c_int),
-        ("kernel_ms", C.c_double),
+        ("kernel_ms", C.c_double), ("cg_force_failures", C.c_int), ("reserved_", C.c_int),
     ]
 
 
@@ -63,6 +63,8 @@ _SIGS = {
     "sm_last_kernel_ms": [ctx_p, dp],
     "sm_launch_count": [ctx_p, C.POINTER(C.c_longlong)],
     "sm_one_pass_dd": [ctx_p, ip],
+    "sm_peer_mode": [ctx_p, ip],
+    "sm_device_count": [ip],
     "sm_tables": [ctx_p, C.c_int, C.c_int, C.c_int, ip, ip, dp, dp, ip, ip],
     "sm_D_phi": [ctx_p, dp, dp, dp, dp, dp, dp, C.c_double],
     "sm_D_dagger_phi": [ctx_p, dp, dp, dp, dp, dp, dp, C.c_double],

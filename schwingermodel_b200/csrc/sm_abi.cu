@@ -6,6 +6,91 @@
 // ================================================================================================
 // extern "C"
 // ================================================================================================
+// ---- peer-memory windows (halo rows and CG sums over NVLink) -----------------------------------------
+static int p2p_make_window(sm_ctx* c, cudaIpcMemHandle_t* h) {
+    if (!c->dist() || c->rt != 1 || c->wx < 4) return fail(SM_ERR_STATE, "peer-memory halos need a lattice split along x only");
+    if (!c->win) {
+        c->win_bytes = win_total_bytes(c);
+        CU(cudaMalloc((void**)&c->win, c->win_bytes));
+        CU(cudaMemset(c->win, 0, c->win_bytes));
+        c->win_flags = win_flag(c, c->win, 0, 0);
+        TRY(dev_alloc(&c->push_ticket, (size_t)1));
+        CU(cudaMemset(c->push_ticket, 0, sizeof(unsigned int)));
+    }
+    CU(cudaIpcGetMemHandle(h, c->win));
+    return SM_OK;
+}
+
+// map the neighbours' windows (halo rows) and, on up to kMaxPeers ranks, every rank's window (CG sums)
+static int p2p_open_windows(sm_ctx* c, const void* all_handles) {
+    if (c->p2p) return SM_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qr) != cudaSuccess || fn == nullptr)
+        return fail(SM_ERR_CUDA, "cuStreamWaitValue32 is not available");
+    c->wait_value32 = (CUresult(*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int))fn;
+    const bool all = c->nranks <= kMaxPeers;
+    std::vector<void*> opened(c->nranks, nullptr);
+    opened[c->rank] = c->win;
+    auto open_rank = [&](int r) -> int {
+        if (opened[r]) return SM_OK;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)all_handles + (size_t)r * SM_P2P_HANDLE_BYTES, sizeof(h));
+        CU(cudaIpcOpenMemHandle(&opened[r], h, cudaIpcMemLazyEnablePeerAccess));
+        return SM_OK;
+    };
+    int rc = SM_OK;
+    for (int r = 0; r < c->nranks && rc == SM_OK; r++)
+        if (all || r == c->nb_xm || r == c->nb_xp) rc = open_rank(r);
+    if (rc != SM_OK) {
+        for (int r = 0; r < c->nranks; r++)
+            if (opened[r] && r != c->rank) cudaIpcCloseMemHandle(opened[r]);
+        cudaGetLastError();
+        return rc;
+    }
+    c->peer_win[0] = opened[c->nb_xm];
+    c->peer_win[1] = opened[c->nb_xp];
+    if (all)
+        for (int r = 0; r < c->nranks; r++) c->peer_all[r] = opened[r];
+    c->p2p = true;
+    c->peer_sums = all && c->fused_tma_or_fused_ok();
+    return SM_OK;
+}
+
+// Called at the end of sm_create_dist on lattices split along x: every rank exports its window, the handles travel
+// by ncclAllGather, every rank maps its peers.  All ranks then agree (ncclAllReduce of a flag) on whether the windows
+// are usable -- ranks in one process, or GPUs without peer access, fall back to NCCL send/recv + all-reduce together.
+static int p2p_auto_connect(sm_ctx* c) {
+    if (c->rt != 1 || c->wx < 4) return SM_OK;
+    if (const char* e = getenv("SM_P2P"))
+        if (atoi(e) == 0) return SM_OK;
+    cudaIpcMemHandle_t h;
+    memset(&h, 0, sizeof(h));
+    int ok = (p2p_make_window(c, &h) == SM_OK) ? 1 : 0;
+    unsigned char* d_handles = nullptr;
+    int* d_ok = nullptr;
+    CU(cudaMalloc((void**)&d_handles, (size_t)c->nranks * SM_P2P_HANDLE_BYTES));
+    CU(cudaMalloc((void**)&d_ok, sizeof(int)));
+    CU(cudaMemcpyAsync(d_handles + (size_t)c->rank * SM_P2P_HANDLE_BYTES, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+    NC(g_nccl.AllGather(d_handles + (size_t)c->rank * SM_P2P_HANDLE_BYTES, d_handles, SM_P2P_HANDLE_BYTES, ncclChar, c->comm, c->stream));
+    std::vector<unsigned char> handles((size_t)c->nranks * SM_P2P_HANDLE_BYTES);
+    CU(cudaMemcpyAsync(handles.data(), d_handles, handles.size(), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (ok && p2p_open_windows(c, handles.data()) != SM_OK) ok = 0;
+    CU(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    NC(g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, c->comm, c->stream));
+    int all_ok = 0;
+    CU(cudaMemcpyAsync(&all_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(d_handles);
+    cudaFree(d_ok);
+    if (!all_ok) {       // together or not at all
+        c->p2p = false;
+        c->peer_sums = false;
+    }
+    return SM_OK;
+}
+
 extern "C" {
 
 const char* sm_last_error(void) { return g_err.c_str(); }
@@ -121,7 +206,7 @@ int sm_create_dist(int Nx, int Nt, int ranks_x, int ranks_t, int rank, int devic
             CU(cudaMemsetAsync(c->f2_d[0][side], 0, sizeof(cplx) * 4 * wt, c->stream));
             CU(cudaMemsetAsync(c->f2_d[1][side], 0, sizeof(cplx) * 4 * wt, c->stream));
         }
-        return SM_OK;
+        return p2p_auto_connect(c);
     };
     rc = body();
     if (rc != SM_OK) {
@@ -137,8 +222,16 @@ int sm_destroy(sm_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->p2p) {
-        cudaIpcCloseMemHandle(c->peer_win[0]);
-        if (c->peer_win[1] != c->peer_win[0]) cudaIpcCloseMemHandle(c->peer_win[1]);
+        std::vector<void*> closed;
+        auto close_once = [&](void* p) {
+            if (p && p != (void*)c->win && std::find(closed.begin(), closed.end(), p) == closed.end()) {
+                cudaIpcCloseMemHandle(p);
+                closed.push_back(p);
+            }
+        };
+        close_once(c->peer_win[0]);
+        close_once(c->peer_win[1]);
+        for (void* p : c->peer_all) close_once(p);
     }
     if (c->win) cudaFree(c->win);
     if (c->push_ticket) cudaFree(c->push_ticket);
@@ -188,7 +281,7 @@ int sm_local_dims(const sm_ctx* c, int dims[4]) {
 
 int sm_set_cg(sm_ctx* c, double tol, int max_iter) {
     NEED(c);
-    if (!(tol > 0) || max_iter < 1) return fail(SM_ERR_ARG, "tol must be > 0 and max_iter >= 1");
+    if (!(tol > 0) || max_iter < 1 || max_iter > 60000) return fail(SM_ERR_ARG, "tol must be > 0 and 1 <= max_iter <= 60000");
     c->tol = tol;
     c->max_iter = max_iter;
     return SM_OK;
@@ -212,6 +305,21 @@ int sm_one_pass_dd(const sm_ctx* c, int* one_pass) {
     NEED(c);
     NEED(one_pass);
     *one_pass = fused_ok(c) ? 1 : 0;
+    return SM_OK;
+}
+
+int sm_device_count(int* n) {
+    NEED(n);
+    *n = 0;
+    cudaError_t e = cudaGetDeviceCount(n);
+    if (e != cudaSuccess) return fail(SM_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    return SM_OK;
+}
+
+int sm_peer_mode(const sm_ctx* c, int* mode) {
+    NEED(c);
+    NEED(mode);
+    *mode = c->peer_sums ? 2 : (c->p2p ? 1 : 0);
     return SM_OK;
 }
 
@@ -254,22 +362,13 @@ int sm_tables(sm_ctx* c, int ranks_x, int ranks_t, int rank, int* RightPB, int* 
     return SM_OK;
 }
 
-// ---- peer-memory halo push ------------------------------------------------------------------------
+// ---- peer-memory windows: the entry points ------------------------------------------------------------
 int sm_p2p_handle(sm_ctx* c, void* handle_out) {
     TRY(set_device(c));
     NEED(handle_out);
-    if (!c->dist() || c->rt != 1 || c->wx < 4) return fail(SM_ERR_STATE, "peer-memory halos need a lattice split along x only");
-    if (!c->win) {
-        c->win_bytes = sizeof(cplx) * 8 * win_ghost_elems(c) + 256;
-        CU(cudaMalloc((void**)&c->win, c->win_bytes));
-        CU(cudaMemset(c->win, 0, c->win_bytes));
-        c->win_flags = win_flag(c, c->win, 0, 0);
-        TRY(dev_alloc(&c->push_ticket, (size_t)1));
-        CU(cudaMemset(c->push_ticket, 0, sizeof(unsigned int)));
-    }
     static_assert(sizeof(cudaIpcMemHandle_t) == SM_P2P_HANDLE_BYTES, "handle size");
     cudaIpcMemHandle_t h;
-    CU(cudaIpcGetMemHandle(&h, c->win));
+    TRY(p2p_make_window(c, &h));
     memcpy(handle_out, &h, sizeof(h));
     return SM_OK;
 }
@@ -278,24 +377,7 @@ int sm_p2p_connect(sm_ctx* c, const void* all_handles) {
     TRY(set_device(c));
     NEED(all_handles);
     if (!c->win) return fail(SM_ERR_STATE, "sm_p2p_handle first");
-    if (c->p2p) return SM_OK;
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qr;
-    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qr) != cudaSuccess || fn == nullptr)
-        return fail(SM_ERR_CUDA, "cuStreamWaitValue32 is not available");
-    c->wait_value32 = (CUresult(*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int))fn;
-    const int nb[2] = {c->nb_xm, c->nb_xp};
-    for (int s = 0; s < 2; s++) {
-        if (s == 1 && nb[1] == nb[0]) {
-            c->peer_win[1] = c->peer_win[0];
-            break;
-        }
-        cudaIpcMemHandle_t h;
-        memcpy(&h, (const char*)all_handles + (size_t)nb[s] * SM_P2P_HANDLE_BYTES, sizeof(h));
-        CU(cudaIpcOpenMemHandle(&c->peer_win[s], h, cudaIpcMemLazyEnablePeerAccess));
-    }
-    c->p2p = true;
-    return SM_OK;
+    return p2p_open_windows(c, all_handles);
 }
 
 // ---- host-buffer operators ---------------------------------------------------------------------
@@ -593,6 +675,8 @@ int sm_hmc_trajectory(sm_ctx* c, sm_traj_result* out) {
     out->dd_applications = acc.dd_apps;
     out->cg_solves = acc.solves;
     out->cg_all_converged = acc.all_ok;
+    out->cg_force_failures = acc.force_fail;
+    out->reserved_ = 0;
     out->kernel_ms = ms;
     c->last_ms = ms;
     c->hmc_has_fields = false;   // pi, chi are consumed: refresh per trajectory (hmc.cpp:154-157)

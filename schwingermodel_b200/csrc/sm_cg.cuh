@@ -85,11 +85,24 @@ static int cg_fused_loop(sm_ctx* c, const C* U, C* r, C* x, C* dbuf0, C* dbuf1, 
     CgState* st = c->cg;
     C* dbuf[2] = {dbuf0, dbuf1};
 
-    // one iteration: A(k) then B(k) (+ the all-reduces of their sums on a split lattice)
+    // one iteration: A(k) then B(k).  On a split lattice either the sums are all-reduced by NCCL after each kernel, or
+    // (peer-memory windows connected, sm_peer.cuh) the kernels gather them themselves and B(k) stores r's boundary rows
+    // into the neighbours' ghosts: then the loop holds no library call and is captured in a graph like on one tile.
+    const bool peer = c->peer_sums && std::is_same<C, cplx>::value;
+    const DistLink dl = peer ? dist_link(c) : DistLink{};
     auto iteration = [&](int k) -> int {
         const int cur = k & 1;
-        TRY((launch_fused<C, FUSED_CG>(c, U, dbuf[cur ^ 1], Ad, m0, sum_target(c, st->dAd), r, x, dbuf[cur], k)));
-        TRY(sum_finish(c, st->dAd, 2));
+        TRY((launch_fused<C, FUSED_CG>(c, U, dbuf[cur ^ 1], Ad, m0, peer ? nullptr : sum_target(c, st->dAd), r, x, dbuf[cur], k)));
+        if (!peer) TRY(sum_finish(c, st->dAd, 2));
+        if constexpr (std::is_same<C, cplx>::value) {
+            if (peer) {
+                k_cg_resid_dist<<<c->flat_blocks_c, kBlock, 0, c->stream>>>(st, cur, r, Ad, c->wx, c->wt, c->V, c->partials,
+                                                                            c->tickets + TK_UPDATE, dl);
+                KCHECK();
+                c->launches++;
+                return SM_OK;
+            }
+        }
         k_cg_resid<C><<<c->flat_blocks_c, kBlock, 0, c->stream>>>(st, cur, r, Ad, n_elems, c->partials,
                                                                   c->tickets + TK_UPDATE, sum_target(c, &st->rr[cur ^ 1]));
         KCHECK();
@@ -102,7 +115,7 @@ static int cg_fused_loop(sm_ctx* c, const C* U, C* r, C* x, C* dbuf0, C* dbuf1, 
     // tolerance live in CgState, so the nodes are iteration- and tolerance-independent)
     cudaGraphExec_t exec = nullptr;
     int graph_kernels = 0;
-    const bool graphs = c->use_graphs && !c->dist() && max_iter > batch;
+    const bool graphs = c->use_graphs && (!c->dist() || peer) && max_iter > batch;
     if (graphs) {
         for (auto& g : c->cg_graphs)
             if (g.U == (const void*)U && g.x == (const void*)x && g.m0 == m0) {
@@ -120,7 +133,7 @@ static int cg_fused_loop(sm_ctx* c, const C* U, C* r, C* x, C* dbuf0, C* dbuf1, 
         int rc = SM_OK;
         for (int i = 0; i < batch && rc == SM_OK; i++) rc = iteration(1 + i);
         if (rc == SM_OK) {
-            k_cg_check_dev<<<1, 1, 0, c->stream>>>(st);
+            k_cg_check_dev<<<1, 1, 0, c->stream>>>(st, dl);
             c->launches++;
         }
         cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
@@ -144,7 +157,7 @@ static int cg_fused_loop(sm_ctx* c, const C* U, C* r, C* x, C* dbuf0, C* dbuf1, 
         } else {
             const int k_end = std::min(max_iter, k + batch);
             for (; k < k_end; k++) TRY(iteration(k));
-            k_cg_check_dev<<<1, 1, 0, c->stream>>>(st);
+            k_cg_check_dev<<<1, 1, 0, c->stream>>>(st, dl);
             KCHECK();
             c->launches++;
         }
@@ -174,13 +187,17 @@ static int dev_cg_fused(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, doub
     TRY(ensure_complex(c, &c->cg_d2));
     TRY(ensure_complex(c, &c->cg_Ad));
     CgState* st = c->cg;
-    k_cg_reset<<<1, 1, 0, c->stream>>>(st, c->tol, c->max_iter);
+    const unsigned int epoch_base = (++c->solve_seq) << 16;     // max_iter <= 10000 per solve (sm_set_cg caps it below 2^16)
+    k_cg_reset<<<1, 1, 0, c->stream>>>(st, c->tol, c->max_iter, epoch_base);
     c->launches++;
     // x = phi ; r = phi - D D^dagger phi ; |phi|^2, |r|^2   (d_0 = r_0 is formed by the first pass)
     TRY((launch_wilson<true, WILSON_PLAIN>(c, U, phi, c->tmp, m0)));
     TRY((launch_wilson<false, WILSON_CGINIT>(c, U, c->tmp, nullptr, m0, phi, c->cg_r, c->cg_d2, x,
                                              sum_target(c, &st->phi_norm2))));
     TRY(sum_finish(c, &st->phi_norm2, 2));
+    // peer-memory halos: r_0's boundary rows into the neighbours' ghosts (parity 0, epoch base + 0); later r_k are
+    // stored by k_cg_resid_dist itself
+    if (c->peer_sums) TRY(p2p_push(c, c->cg_r, 1, c->stream, (long long)epoch_base, 0));
     TRY(cg_fused_loop<cplx>(c, U, c->cg_r, x, c->cg_d, c->cg_d2, c->cg_Ad, m0, c->max_iter));
     if (converged) *converged = c->h->cg[0].converged;
     if (iterations) *iterations = c->h->cg[0].iters;
@@ -272,27 +289,45 @@ static int resident_finish(sm_ctx* c, int* converged, int* iterations) {
     return SM_OK;
 }
 
-static int dev_cg_cluster(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, int* converged, int* iterations) {
-    ResidentCgArgs a;
-    TRY(resident_args(c, U, phi, x, m0, &a));
+static void cluster_launch_config(sm_ctx* c, cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr) {
     int ctas = 1;
     while (ctas * kClusterThreads < c->V) ctas *= 2;
-    if (!(c->attr_done & (1u << 8))) {
-        CU(cudaFuncSetAttribute(k_cg_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        c->attr_done |= 1u << 8;
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(ctas, 1, 1);
-    cfg.blockDim = dim3(kClusterThreads, 1, 1);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = c->stream;
-    cudaLaunchAttribute attr[1];
+    *cfg = cudaLaunchConfig_t{};
+    cfg->gridDim = dim3(ctas, 1, 1);
+    cfg->blockDim = dim3(kClusterThreads, 1, 1);
+    cfg->dynamicSmemBytes = 0;
+    cfg->stream = c->stream;
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = ctas;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg->attrs = attr;
+    cfg->numAttrs = 1;
+}
+
+// can this device co-schedule the (non-portable, up to 16 CTAs) cluster the lattice needs?  Asked once per context;
+// a MIG slice or a part with fewer SMs per GPC answers no, and the solve takes the cooperative-grid or one-pass path.
+static bool cluster_ok(sm_ctx* c) {
+    if (c->cluster_ok < 0) {
+        c->cluster_ok = 0;
+        if (cudaFuncSetAttribute(k_cg_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+            cudaLaunchConfig_t cfg;
+            cudaLaunchAttribute attr[1];
+            cluster_launch_config(c, &cfg, attr);
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, k_cg_cluster, &cfg) == cudaSuccess && n >= 1) c->cluster_ok = 1;
+        }
+        cudaGetLastError();
+    }
+    return c->cluster_ok == 1;
+}
+
+static int dev_cg_cluster(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, int* converged, int* iterations) {
+    ResidentCgArgs a;
+    TRY(resident_args(c, U, phi, x, m0, &a));
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    cluster_launch_config(c, &cfg, attr);
     CU(cudaLaunchKernelEx(&cfg, k_cg_cluster, a));
     return resident_finish(c, converged, iterations);
 }
@@ -411,7 +446,7 @@ static int dev_cg_cols(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, doubl
 static int dev_cg(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, int* converged, int* iterations) {
     if (c->use_cluster && !c->dist()) {
         if (cols_plan(c) >= 0) return dev_cg_cols(c, U, phi, x, m0, converged, iterations);
-        if (c->V <= kClusterMaxCtas * kClusterThreads) return dev_cg_cluster(c, U, phi, x, m0, converged, iterations);
+        if (c->V <= kClusterMaxCtas * kClusterThreads && cluster_ok(c)) return dev_cg_cluster(c, U, phi, x, m0, converged, iterations);
         if (c->V <= coop_capacity(c)) return dev_cg_coop(c, U, phi, x, m0, converged, iterations);   // width_t < 32 or SM_COLS=0
     }
     if (c->solver == SM_SOLVER_MIXED && fused_ok(c) && !c->dist()) return dev_cg_mixed(c, U, phi, x, m0, converged, iterations);

@@ -83,9 +83,11 @@ __device__ __forceinline__ double warp_sum(double v) {
 // through the returned values in `v`).
 // A reduction may span several launches (interior + boundary blocks of one pass): they share the
 // ticket, and pass the total block count and their global block index explicitly.
+// `sys_scope`: the block's earlier stores include stores into a peer GPU's memory that the finishing block is about
+// to release with a flag there, so the fence before the ticket must be system-wide.
 template <int NS>
 __device__ __forceinline__ bool grid_reduce(double (&v)[NS], double* __restrict__ partials, unsigned int* ticket,
-                                            int nblocks = -1, int bid = -1) {
+                                            int nblocks = -1, int bid = -1, bool sys_scope = false) {
     __shared__ double s_part[kWarps][NS];
     __shared__ bool s_last;
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
@@ -111,7 +113,8 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NS], double* __restrict_
             if (lane == 0) partials[NS * bid + j] = x;
         }
         if (lane == 0) {
-            __threadfence();
+            if (sys_scope) __threadfence_system();
+            else __threadfence();
             const unsigned int t = atomicAdd(ticket, 1u);
             s_last = (t == (unsigned int)(nblocks - 1));
         }

@@ -19,6 +19,7 @@
 
 #include "sm_kernels.cuh"
 #include "sm_fused.cuh"
+#include "sm_fused_tma.cuh"
 #include "sm_cluster_cg.cuh"
 
 using namespace sm;
@@ -62,6 +63,7 @@ struct NcclApi {
     decltype(&ncclSend) Send = nullptr;
     decltype(&ncclRecv) Recv = nullptr;
     decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
     decltype(&ncclGroupStart) GroupStart = nullptr;
     decltype(&ncclGroupEnd) GroupEnd = nullptr;
     decltype(&ncclGetErrorString) GetErrorString = nullptr;
@@ -76,7 +78,7 @@ static int nccl_load() {
 #define BIND(name)                                                             \
     g_nccl.name = (decltype(g_nccl.name))dlsym(h, "nccl" #name);               \
     if (!g_nccl.name) return fail(SM_ERR_NCCL, "libnccl lacks nccl" #name);
-    BIND(GetUniqueId) BIND(CommInitRank) BIND(CommDestroy) BIND(Send) BIND(Recv) BIND(AllReduce) BIND(GroupStart)
+    BIND(GetUniqueId) BIND(CommInitRank) BIND(CommDestroy) BIND(Send) BIND(Recv) BIND(AllReduce) BIND(AllGather) BIND(GroupStart)
     BIND(GroupEnd) BIND(GetErrorString)
 #undef BIND
     g_nccl.handle = h;
@@ -117,6 +119,8 @@ struct sm_ctx {
     int fus_rows = 0, fus_cols = 0;
     int fus_rb = 8, fus_split_rows = 0, fus_split_chunks = 0;   // interior/boundary launch split (split lattice)
     bool use_fused = true;      // SM_DD_PATH=twopass selects the two-pass form
+    bool fused_tma = true;      // rows staged by TMA bulk copies (k_dd_tma); SM_FUSED_TMA=0: per-thread cp.async (k_dd_fused)
+    int fused_stages = 4;       // rows of shared-memory staging per block in k_dd_tma<PLAIN/DOT> (SM_FUSED_STAGES=3|4)
     int flat_blocks_c = 0;   // grid for flat passes over 2V elements
     int flat_blocks_s = 0;   // grid for passes over V sites
 
@@ -161,7 +165,10 @@ struct sm_ctx {
     unsigned int* win_flags = nullptr;
     size_t win_bytes = 0;
     void* peer_win[2] = {nullptr, nullptr};   // -x, +x neighbour's window (peer pointers)
+    void* peer_all[kMaxPeers] = {nullptr};    // every rank's window as seen from here ([rank] = win); peer sums only
     bool p2p = false;
+    bool peer_sums = false;                   // CG sums gathered through the windows (all ranks mapped): no NCCL in the loop
+    unsigned int solve_seq = 0;               // CG solves so far: epochs of a solve are (solve_seq << 16) + k
     unsigned int p2p_epoch[2] = {0, 0};
     unsigned int* push_ticket = nullptr;
     CUresult (*wait_value32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
@@ -183,6 +190,7 @@ struct sm_ctx {
     cplxf *mx_U = nullptr, *mx_r = nullptr, *mx_e = nullptr, *mx_d0 = nullptr, *mx_d1 = nullptr, *mx_Ad = nullptr;
     bool use_cluster = true;   // whole-solve resident kernels for small lattices (SM_CLUSTER_CG=0 disables)
     int coop_sites = -1;
+    int cluster_ok = -1;       // -1 not asked yet; can the device schedule k_cg_cluster's cluster (cudaOccupancyMaxActiveClusters)
     // several rows per thread (k_cg_cols): variant chosen once per context (cols_plan)
     bool cols_planned = false, cols_enabled = true;
     int cols = -1, cols_force_S = 0, cols_force_T = 0;
@@ -193,6 +201,7 @@ struct sm_ctx {
     unsigned int* coop_bar = nullptr;
 
     bool dist() const { return nranks > 1; }
+    bool fused_tma_or_fused_ok() const { return use_fused; }
     double sR_edge() const { return (ct == rt - 1) ? -1.0 : 1.0; }
     double sL_edge() const { return (ct == 0) ? -1.0 : 1.0; }
 };
@@ -238,6 +247,8 @@ static int ctx_common_init(sm_ctx* c) {
     CU(cudaEventCreateWithFlags(&c->ev_ghost, cudaEventDisableTiming));
     if (const char* e = getenv("SM_OVERLAP")) c->overlap = atoi(e) != 0;
     if (const char* e = getenv("SM_GRAPHS")) c->use_graphs = atoi(e) != 0;
+    if (const char* e = getenv("SM_FUSED_TMA")) c->fused_tma = atoi(e) != 0;
+    if (const char* e = getenv("SM_FUSED_STAGES")) c->fused_stages = atoi(e) == 3 ? 3 : 4;
     if (const char* e = getenv("SM_CLUSTER_CG")) c->use_cluster = atoi(e) != 0;
     if (const char* e = getenv("SM_COLS")) {      // "0": off; "S,T": force a variant
         int S = 0, T = 512;

@@ -63,6 +63,7 @@ struct FusedArgsT {
     const C* gr_hi;
     C* gd_lo;          // CG: ghost rows of d_k, written here for the next iteration
     C* gd_hi;
+    DistLink dl;       // CG on a split lattice with peer-memory sums and halos (sm_peer.cuh); dl.on == 0 otherwise
 };
 
 typedef FusedArgsT<cplx> FusedArgs;
@@ -82,6 +83,64 @@ struct Hop {
     template <typename C> static __device__ __forceinline__ void add_tm(C v, C& a0, C& a1) { const typename RealOf<C>::type s = si; a0 = cadd(a0, v); a1.x -= s * v.x; a1.y -= s * v.y; }
     template <typename C> static __device__ __forceinline__ void add_xm(C v, C& a0, C& a1) { const typename RealOf<C>::type s = si; a0 = cadd(a0, v); a1.x += s * v.y; a1.y -= s * v.x; }
 };
+
+// Start of a FUSED_CG pass (iteration k): the stopping rule of iteration k-1 and the scalars beta_k, alpha_{k-1}
+// (src/conjugate_gradient.cpp:43-53).  On a split lattice with peer-memory sums |r_k|^2 is still spread over the
+// ranks' slots (k_cg_resid of iteration k-1 published it): every block gathers it, the lead block files it in
+// CgState.  Returns false when the whole block has to leave (solve finished).  Called by all threads.
+template <typename C>
+__device__ __forceinline__ bool fused_cg_begin(const FusedArgsT<C>& a, bool lead_thread, typename RealOf<C>::type& beta,
+                                               C& alpha, bool& first) {
+    typedef typename RealOf<C>::type R;
+    if (a.st->done) return false;
+    const int cur = a.cur;
+    first = (a.first != 0);
+    if (first) return true;
+    double rr_cur;
+    if (a.dl.on) {
+        double g[1];
+        gather_sums<1>(a.dl, 1, cur ^ 1, a.st->epoch_base + (unsigned int)a.st->k, g);
+        rr_cur = g[0];
+        if (lead_thread) a.st->rr[cur] = rr_cur;
+    } else {
+        rr_cur = a.st->rr[cur];
+    }
+    if (sqrt(rr_cur) < a.st->tol * sqrt(a.st->phi_norm2)) {
+        if (lead_thread) {
+            a.st->iters = a.st->k - 1;
+            a.st->converged = 1;
+            a.st->done = 1;
+        }
+        return false;
+    }
+    beta = (R)(rr_cur / a.st->rr[cur ^ 1]);
+    alpha = mkc<C>((R)a.st->alpha[0], (R)a.st->alpha[1]);
+    return true;
+}
+
+// blocks that read ghost rows of r wait until both neighbours have delivered r_k (epoch base + k)
+template <typename C>
+__device__ __forceinline__ void fused_cg_wait_ghosts(const FusedArgsT<C>& a) {
+    if (a.dl.on && a.gU_lo != nullptr && a.chunk_mode != 1) {
+        if (threadIdx.x == 0) {
+            const unsigned int e = a.st->epoch_base + (unsigned int)a.st->k;
+            spin_until(a.dl.my_flag_lo, e);
+            spin_until(a.dl.my_flag_hi, e);
+        }
+        __syncthreads();
+    }
+}
+
+// the finishing block of a FUSED_DOT / FUSED_CG pass files dot(d, A d): CgState (or the caller's buffer), or the ranks' slots
+template <typename C>
+__device__ __forceinline__ void fused_sums_out(const FusedArgsT<C>& a, const double (&acc)[2]) {
+    if (a.dl.on) {
+        publish_sums<2>(a.dl, 0, a.cur, a.st->epoch_base + (unsigned int)a.st->k + 1u, acc);
+    } else {
+        a.sums_out[0] = acc[0];
+        a.sums_out[1] = acc[1];
+    }
+}
 
 __device__ __forceinline__ int wrap_idx(int a, int n) {
     a %= n;
@@ -130,21 +189,8 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_fused(const FusedArgsT<C> a) {
     C alpha = mkc<C>(0, 0);
     bool first = true;
     if (MODE == FUSED_CG) {
-        if (a.st->done) return;
-        const int cur = a.cur;
-        first = (a.first != 0);
-        if (!first) {
-            if (cg_converged(a.st, cur, a.st->tol)) {
-                if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0 && a.chunk_mode != 1) {
-                    a.st->iters = a.st->k - 1;
-                    a.st->converged = 1;
-                    a.st->done = 1;
-                }
-                return;
-            }
-            beta = (R)(a.st->rr[cur] / a.st->rr[cur ^ 1]);
-            alpha = mkc<C>((R)a.st->alpha[0], (R)a.st->alpha[1]);
-        }
+        if (!fused_cg_begin(a, blockIdx.x == 0 && blockIdx.y == 0 && tid == 0 && a.chunk_mode != 1, beta, alpha, first)) return;
+        fused_cg_wait_ghosts(a);
     }
 
     const int tc = blockIdx.x * a.cols_per_strip - 2 + tid;    // unwrapped column of this thread
@@ -327,10 +373,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_fused(const FusedArgsT<C> a) {
 
     if (MODE != FUSED_PLAIN) {
         if (grid_reduce<2>(acc, a.partials, a.ticket, (int)gridDim.x * a.nchunks, chunk * (int)gridDim.x + (int)blockIdx.x)) {
-            if (tid == 0) {
-                a.sums_out[0] = acc[0];
-                a.sums_out[1] = acc[1];
-            }
+            if (tid == 0) fused_sums_out(a, acc);
         }
     }
 }
@@ -361,6 +404,63 @@ __global__ void __launch_bounds__(kBlock) k_cg_resid(CgState* st, int cur, C* __
             st->pending = 1;        // x still lacks alpha_k d_k
             st->pending_buf = cur;  // d_k lives in d buffer (k & 1)
             st->k = st->k + 1;
+        }
+    }
+}
+
+// The same on a lattice split along x with peer-memory sums and halos (sm_peer.cuh): dot(d, A d) is gathered from the
+// ranks' slots; the two boundary rows of r on each side are updated FIRST and stored into the neighbours' ghost rows as
+// they are formed ([component][2 rows][wt], parity of iteration k+1), then the interior; the finishing block
+// publishes |r|^2 and raises the neighbours' ghost flags (epoch base + k + 1).
+__global__ void __launch_bounds__(kBlock) k_cg_resid_dist(CgState* st, int cur, cplx* __restrict__ r, const cplx* __restrict__ Ad,
+                                                          int wx, int wt, int V, double* partials, unsigned int* ticket,
+                                                          const DistLink dl) {
+    if (st->done) return;
+    double g[2];
+    gather_sums<2>(dl, 0, cur, st->epoch_base + (unsigned int)st->k + 1u, g);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->dAd[0] = g[0];
+        st->dAd[1] = g[1];
+    }
+    const cplx alpha = cdiv(make_double2(st->rr[cur], 0.0), make_double2(g[0], g[1]));
+    double acc[1] = {0.0};
+    const int stride = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    cplx* __restrict__ to_xm = dl.push_xm_hi[cur ^ 1];
+    cplx* __restrict__ to_xp = dl.push_xp_lo[cur ^ 1];
+    const int per_side = 4 * wt;
+    for (int i = gtid; i < 2 * per_side; i += stride) {
+        const int side = i / per_side, e = i - side * per_side;
+        const int comp = e / (2 * wt), off = e - comp * 2 * wt;
+        const size_t idx = (size_t)comp * V + (side == 0 ? 0 : (size_t)(wx - 2) * wt) + off;
+        const cplx av = ld_stream(Ad + idx);
+        cplx rv = r[idx];
+        rv = csub(rv, cmul(alpha, av));
+        r[idx] = rv;
+        (side == 0 ? to_xm : to_xp)[e] = rv;
+        acc[0] += rv.x * rv.x + rv.y * rv.y;
+    }
+    const int vint = (wx - 4) * wt;     // rows 2 .. wx-3 of one component
+    for (int i = gtid; i < 2 * vint; i += stride) {
+        const int comp = (i >= vint) ? 1 : 0;
+        const size_t idx = (size_t)comp * V + 2 * (size_t)wt + (size_t)(i - comp * vint);
+        const cplx av = ld_stream(Ad + idx);
+        cplx rv = r[idx];
+        rv = csub(rv, cmul(alpha, av));
+        r[idx] = rv;
+        acc[0] += rv.x * rv.x + rv.y * rv.y;
+    }
+    if (grid_reduce<1>(acc, partials, ticket, -1, -1, true)) {
+        if (threadIdx.x == 0) {
+            const unsigned int e = st->epoch_base + (unsigned int)st->k + 1u;
+            st->alpha[0] = alpha.x;
+            st->alpha[1] = alpha.y;
+            st->pending = 1;
+            st->pending_buf = cur;
+            st->k = st->k + 1;
+            publish_sums<1>(dl, 1, cur, e, acc);
+            __threadfence_system();
+            st_release_sys(dl.flag_xm, e);
+            st_release_sys(dl.flag_xp, e);
         }
     }
 }

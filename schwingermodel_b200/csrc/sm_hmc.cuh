@@ -219,6 +219,7 @@ struct TrajAcc {
     long long dd_apps = 0;
     int solves = 0;
     int all_ok = 1;
+    int force_fail = 0;   // non-converged solves inside HMC::Force (the reference dumps an illConf for each, hmc.cpp:48-56)
 };
 
 static int hmc_alloc(sm_ctx* c) {
@@ -244,6 +245,7 @@ static int hmc_force(sm_ctx* c, const cplx* U, const cplx* phi, double* F, TrajA
         acc->dd_apps += ok ? its + 2 : its + 1;
         acc->solves++;
         acc->all_ok &= ok;
+        acc->force_fail += ok ? 0 : 1;
     }
     TRY(dev_D(c, U, c->psi, c->xi, c->hp.m0, true));
     return dev_force(c, U, c->psi, c->xi, F, c->hp.beta, true, true);

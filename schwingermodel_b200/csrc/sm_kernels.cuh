@@ -11,6 +11,7 @@
 // site n = x*wt + t.  This is the reference's spinor{mu0,mu1} / re_field (include/variables.h:54-141).
 #pragma once
 #include "sm_common.cuh"
+#include "sm_peer.cuh"
 
 namespace sm {
 
@@ -62,6 +63,7 @@ struct CgState {
     int k;              // iteration counter kept on the device (one-pass path: kernels are replayed from a CUDA graph)
     int max_iter;       // one-pass path: iteration limit of the running solve (kept here so graphs do not bake it)
     double tol;         // ... and its relative tolerance
+    unsigned int epoch_base;   // split lattice with peer-memory sums: epochs of this solve are epoch_base + k (+1)
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -412,10 +414,12 @@ __global__ void k_cg_check(CgState* st, int k, double tol, int max_iter) {
     }
 }
 
-// the same with the device-side iteration counter (one-pass path)
-__global__ void k_cg_check_dev(CgState* st) {
+// the same with the device-side iteration counter (one-pass path).  With peer-memory sums the |r|^2 of the last
+// iteration is still in the ranks' slots: gather it (kind 1, parity of iteration k-1, epoch base + k).
+__global__ void k_cg_check_dev(CgState* st, const DistLink dl) {
     if (st->done) return;
     const int k = st->k, max_iter = st->max_iter;
+    if (dl.on && k > 0) st->rr[k & 1] = gather_sum1_thread(dl, 1, (k - 1) & 1, st->epoch_base + (unsigned int)k);
     if (cg_converged(st, k & 1, st->tol)) {
         st->iters = k - 1;
         st->converged = 1;
@@ -427,7 +431,8 @@ __global__ void k_cg_check_dev(CgState* st) {
     }
 }
 
-__global__ void k_cg_reset(CgState* st, double tol, int max_iter) {
+__global__ void k_cg_reset(CgState* st, double tol, int max_iter, unsigned int epoch_base = 0) {
+    st->epoch_base = epoch_base;
     st->tol = tol;
     st->max_iter = max_iter;
     st->done = 0;

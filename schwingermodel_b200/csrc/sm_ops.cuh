@@ -83,11 +83,37 @@ static cplx* win_ghost(const sm_ctx* c, void* base, int kind, int parity, int si
 static unsigned int* win_flag(const sm_ctx* c, void* base, int kind, int side) {
     return (unsigned int*)((char*)base + sizeof(cplx) * 8 * win_ghost_elems(c)) + kind * 2 + side;
 }
+static SumSlot* win_slots(const sm_ctx* c, void* base) {
+    return (SumSlot*)((char*)base + sizeof(cplx) * 8 * win_ghost_elems(c) + 256);
+}
+static size_t win_total_bytes(const sm_ctx* c) {
+    return sizeof(cplx) * 8 * win_ghost_elems(c) + 256 + sizeof(SumSlot) * 4 * kMaxPeers;
+}
+
+// what the CG kernels need to do their own collectives (sm_peer.cuh)
+static DistLink dist_link(const sm_ctx* c) {
+    DistLink dl{};
+    if (!c->peer_sums) return dl;
+    dl.on = 1;
+    dl.nranks = c->nranks;
+    dl.rank = c->rank;
+    dl.mine = win_slots(c, c->win);
+    for (int r = 0; r < c->nranks; r++) dl.peer[r] = win_slots(c, c->peer_all[r]);
+    for (int parity = 0; parity < 2; parity++) {
+        dl.push_xm_hi[parity] = win_ghost(c, c->peer_win[0], 1, parity, 1);
+        dl.push_xp_lo[parity] = win_ghost(c, c->peer_win[1], 1, parity, 0);
+    }
+    dl.flag_xm = win_flag(c, c->peer_win[0], 1, 1);
+    dl.flag_xp = win_flag(c, c->peer_win[1], 1, 0);
+    dl.my_flag_lo = win_flag(c, c->win, 1, 0);
+    dl.my_flag_hi = win_flag(c, c->win, 1, 1);
+    return dl;
+}
 
 // push my boundary rows of `field` into both neighbours' ghosts (epoch parity) and raise their flags
-static int p2p_push(sm_ctx* c, const cplx* field, int kind, cudaStream_t st) {
-    const unsigned int epoch = ++c->p2p_epoch[kind];
-    const int parity = epoch & 1;
+static int p2p_push(sm_ctx* c, const cplx* field, int kind, cudaStream_t st, long long fixed_epoch = -1, int fixed_parity = 0) {
+    const unsigned int epoch = fixed_epoch >= 0 ? (unsigned int)fixed_epoch : ++c->p2p_epoch[kind];
+    const int parity = fixed_epoch >= 0 ? fixed_parity : (int)(epoch & 1);
     const int n = 8 * c->wt;
     const int blocks = std::max(1, std::min(64, (n + kBlock - 1) / kBlock));
     k_push_rows<<<blocks, kBlock, 0, st>>>(field, c->wx, c->wt, c->V, win_ghost(c, c->peer_win[0], kind, parity, 1),
@@ -161,10 +187,25 @@ static int launch_fused(sm_ctx* c, const C* U, const C* in, C* out, double m0, d
     // rows in flight per block: as many as 2 blocks per SM leave shared memory for (single precision moves
     // half the bytes per row, so it keeps more rows in flight)
     constexpr int STAGES = kDouble ? ((MODE == FUSED_CG) ? 2 : 3) : 3;
-    const size_t smem = fused_smem_bytes(MODE, STAGES, c->fus_block.x, sizeof(C));
-    const unsigned int attr_bit = 1u << (MODE + (kDouble ? 0 : 4));
+    size_t smem = fused_smem_bytes(MODE, STAGES, c->fus_block.x, sizeof(C));
+    // double precision: rows staged by TMA bulk copies (sm_fused_tma.cuh) unless SM_FUSED_TMA=0
+    void (*kern)(const FusedArgsT<C>) = k_dd_fused<C, MODE, STAGES>;
+    unsigned int attr_bit = 1u << (MODE + (kDouble ? 0 : 4));
+    if constexpr (kDouble) {
+        if (c->fused_tma) {
+            if (MODE != FUSED_CG && c->fused_stages == 4) {
+                kern = k_dd_tma<MODE, (MODE == FUSED_CG) ? 2 : 4>;
+                smem = fused_tma_smem_bytes(MODE, (MODE == FUSED_CG) ? 2 : 4, c->fus_block.x);
+                attr_bit = 1u << (16 + MODE);
+            } else {
+                kern = k_dd_tma<MODE, STAGES>;
+                smem = fused_tma_smem_bytes(MODE, STAGES, c->fus_block.x);
+                attr_bit = 1u << (12 + MODE);
+            }
+        }
+    }
     if (!(c->attr_done & attr_bit)) {   // function attributes are per device: once per context and instantiation
-        CU(cudaFuncSetAttribute(k_dd_fused<C, MODE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         c->attr_done |= attr_bit;
     }
     bool split_launch = false;
@@ -184,12 +225,20 @@ static int launch_fused(sm_ctx* c, const C* U, const C* in, C* out, double m0, d
             cplx* dst[2] = {(MODE == FUSED_CG) ? c->f2_r[0] : c->f2_in[0], (MODE == FUSED_CG) ? c->f2_r[1] : c->f2_in[1]};
             split_launch = c->overlap && c->fus_split_chunks >= 1;
             cudaStream_t xs = split_launch ? c->comm_stream : c->stream;
-            if (c->p2p) TRY(p2p_push(c, moving, kind, c->stream));   // stores into the neighbours' windows
+            // CG with peer-memory sums: r's ghost rows were stored into my window by the neighbours' k_cg_resid (or by
+            // the push that starts the solve) and the kernel itself waits for them -- nothing to exchange here
+            const bool in_kernel = (MODE == FUSED_CG) && c->peer_sums;
             if (split_launch) {
                 CU(cudaEventRecord(c->ev_ready, c->stream));
                 CU(cudaStreamWaitEvent(c->comm_stream, c->ev_ready, 0));
             }
-            if (c->p2p) {
+            if (in_kernel) {
+                const int cur = k & 1;
+                dst[0] = win_ghost(c, c->win, 1, cur, 0);
+                dst[1] = win_ghost(c, c->win, 1, cur, 1);
+                a.dl = dist_link(c);
+            } else if (c->p2p) {
+                TRY(p2p_push(c, moving, kind, xs));                   // stores into the neighbours' windows
                 TRY(p2p_wait(c, kind, xs));                           // ... and waits for theirs in mine
                 const int parity = c->p2p_epoch[kind] & 1;
                 dst[0] = win_ghost(c, c->win, kind, parity, 0);
@@ -217,16 +266,16 @@ static int launch_fused(sm_ctx* c, const C* U, const C* in, C* out, double m0, d
         a.rows_per_block = c->fus_split_rows;
         a.nchunks = c->fus_split_chunks + 2;
         a.chunk_mode = 2;
-        k_dd_fused<C, MODE, STAGES><<<dim3(c->fus_grid.x, 2, 1), c->fus_block, smem, c->comm_stream>>>(a);
+        kern<<<dim3(c->fus_grid.x, 2, 1), c->fus_block, smem, c->comm_stream>>>(a);
         KCHECK();
         CU(cudaEventRecord(c->ev_ghost, c->comm_stream));
         a.chunk_mode = 1;
-        k_dd_fused<C, MODE, STAGES><<<dim3(c->fus_grid.x, c->fus_split_chunks, 1), c->fus_block, smem, c->stream>>>(a);
+        kern<<<dim3(c->fus_grid.x, c->fus_split_chunks, 1), c->fus_block, smem, c->stream>>>(a);
         KCHECK();
         CU(cudaStreamWaitEvent(c->stream, c->ev_ghost, 0));
         c->launches += 2;
     } else {
-        k_dd_fused<C, MODE, STAGES><<<c->fus_grid, c->fus_block, smem, c->stream>>>(a);
+        kern<<<c->fus_grid, c->fus_block, smem, c->stream>>>(a);
         KCHECK();
         c->launches++;
     }

@@ -154,6 +154,12 @@ class Lattice:
         check(self.lib.sm_one_pass_dd(self.ctx, C.byref(v)))
         return bool(v.value)
 
+    def peer_mode(self) -> int:
+        """0: single tile / NCCL; 1: halo rows by peer-memory stores; 2: halos and CG sums by the kernels over peer memory."""
+        v = C.c_int()
+        check(self.lib.sm_peer_mode(self.ctx, C.byref(v)))
+        return v.value
+
     def new_field(self, complex_field=True, init=None) -> DeviceField:
         f = DeviceField(self, complex_field)
         if init is not None:

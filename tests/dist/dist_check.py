@@ -38,20 +38,27 @@ def check_lattice(nx, nt, decomps, rank, world, local):
     report = []
     # every decomposition with the default path choice, and the x-only splits again with the one-pass
     # D D^dagger forced (2-row ghosts), which small lattices would not pick on their own
-    cases = [(rx, rt, None) for rx, rt in decomps] + [(rx, rt, "onepass") for rx, rt in decomps if rt == 1 and rx > 1]
-    cases += [(rx, rt, "onepass+p2p") for rx, rt in decomps if rt == 1 and rx > 1 and nx // rx >= 4]
+    # x-only splits connect peer-memory windows by default (halo rows and CG sums by the kernels themselves, CG batches
+    # as CUDA graphs); "nccl" runs them again with SM_P2P=0 (ncclSend/Recv halos, ncclAllReduce sums, plain launches),
+    # "p2p-explicit" through the sm_p2p_handle / sm_p2p_connect entry points
+    cases = [(rx, rt, None) for rx, rt in decomps] + [(rx, rt, "nccl") for rx, rt in decomps if rt == 1 and rx > 1]
+    cases += [(rx, rt, "p2p-explicit") for rx, rt in decomps if rt == 1 and rx > 1 and nx // rx >= 4]
     for rx, rt, path in cases:
-        if path:
-            os.environ["SM_DD_PATH"] = "onepass"
+        os.environ["SM_P2P"] = "1" if path is None else "0"
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             idt.copy_(torch.frombuffer(bytearray(sb.Lattice.nccl_unique_id()), dtype=torch.uint8))
         dist.broadcast(idt, 0)
         lat = sb.Lattice(nx, nt, device=local, ranks_x=rx, ranks_t=rt, rank=rank, nccl_id=idt.cpu().numpy().tobytes())
-        os.environ.pop("SM_DD_PATH", None)
+        os.environ.pop("SM_P2P", None)
         one_pass = lat.one_pass_dd()
-        if path == "onepass+p2p":
+        if path == "p2p-explicit":
             lat.p2p_connect_all(dist)     # halo rows by peer-memory stores instead of NCCL send/recv
+        peer_mode = lat.peer_mode()
+        if path is None and rt == 1 and rx > 1 and nx // rx >= 4:
+            assert peer_mode == 2, peer_mode          # the default on x-only splits: everything over peer memory
+        if path == "nccl":
+            assert peer_mode == 0
         T = lambda f: tile_of(f, nx, nt, rx, rt, rank)   # noqa: E731
         tabs, otabs = lat.periodic_boundary(rx, rt, rank), P.tables(rx, rt, rank)
         assert all(np.array_equal(tabs[k], otabs[k]) for k in tabs)
@@ -97,7 +104,7 @@ def check_lattice(nx, nt, decomps, rank, world, local):
         tol["pi'"] = 1e-8
         bad = {k: v for k, v in e.items() if not v <= tol[k]}
         report.append({"lattice": [nx, nt], "ranks_x": rx, "ranks_t": rt, "path": path or "default",
-                       "one_pass": one_pass, "errors": e, "bad": bad})
+                       "one_pass": one_pass, "peer_mode": peer_mode, "errors": e, "bad": bad})
         assert not bad, (rx, rt, bad)
         dist.barrier()
     return report
