@@ -683,6 +683,34 @@ def extra_metrics(sb, args):
     for _ in range(ntr):
         h.HMC_Update()
     dt = time.perf_counter() - t0
+    # the same with the opt-in chronological start vectors (a different iterate, so not used by any other number)
+    hc = sb.HMC(lat, synthetic_links(n * n, 4), 20, 1.0, 0, 0, 0, 2.0, -0.18, seed=12)
+    lat.set_solver("chrono")
+    hc.HMC_Update()
+    t0c = time.perf_counter()
+    for _ in range(ntr):
+        hc.HMC_Update()
+    dtc = time.perf_counter() - t0c
+    lat.set_solver("reference")
+    out["hmc_512_near_critical_chrono_opt_in"] = {"traj_per_s": ntr / dtc,
+                                                  "dd_applications_per_traj": int(np.mean([x[2] for x in hc.history[1:]])),
+                                                  "all_cg_converged": all(x[3] for x in hc.history),
+                                                  "note": "sm_set_solver(SM_SOLVER_CHRONO): force solves start from the "
+                                                          "extrapolated previous solutions"}
+    # ... and the opt-in even-odd HMC (pseudofermion on the even sites, CG on the Schur complement: a different Markov chain
+    # with the same stationary distribution; not used by any other number of this line)
+    lat.set_solver("evenodd")
+    he = sb.HMC(lat, synthetic_links(n * n, 4), 20, 1.0, 0, 0, 0, 2.0, -0.18, seed=12)
+    he.HMC_Update()
+    t0e = time.perf_counter()
+    for _ in range(ntr):
+        he.HMC_Update()
+    dte = time.perf_counter() - t0e
+    lat.set_solver("reference")
+    out["hmc_512_near_critical_evenodd_opt_in"] = {"traj_per_s": ntr / dte,
+                                                   "schur_applications_per_traj": int(np.mean([x[2] for x in he.history[1:]])),
+                                                   "all_cg_converged": all(x[3] for x in he.history),
+                                                   "note": "sm_set_solver(SM_SOLVER_EVENODD)"}
     out["hmc_512_near_critical"] = {"traj_per_s": ntr / dt,
                                     "dd_applications_per_traj": int(np.mean([x[2] for x in h.history[1:]])),
                                     "kernel_ms_per_traj": float(np.mean([x[4] for x in h.history[1:]])),

@@ -86,8 +86,18 @@ SM_API int sm_set_cg(sm_ctx* ctx, double tol, int max_iter);
  *   SM_SOLVER_REFERENCE  the reference's algorithm in double precision (default; dH parity <= 1e-8)
  *   SM_SOLVER_MIXED      opt-in: single-precision inner CG inside a double-precision defect correction
  *                        (lattices above ~75k sites on a single tile); same stopping criterion, checked on the
- *                        TRUE residual, but a different iterate than the reference's */
-enum { SM_SOLVER_REFERENCE = 0, SM_SOLVER_MIXED = 1 };
+ *                        TRUE residual, but a different iterate than the reference's
+ *   SM_SOLVER_CHRONO     opt-in: the reference's CG arithmetic and stopping rule, but inside a trajectory the solves of
+ *                        HMC::Force (and the proposal's HMC::Action) start from the previous solution / the linear
+ *                        extrapolation of the last two instead of from phi (conjugate_gradient.cpp:16): fewer iterations,
+ *                        a different iterate, dH differs at the CG-truncation level
+ *   SM_SOLVER_EVENODD    opt-in: even-odd preconditioned HMC.  The pseudofermion lives on the even sites with the action
+ *                        phi_e^dagger (Dhat Dhat^dagger)^-1 phi_e, Dhat = m - (1/4m) H_eo H_oe the Schur complement of D
+ *                        (same determinant as D D^dagger up to a constant, hence the same gauge-field distribution);
+ *                        every solve is a CG on half the sites with a ~4x smaller condition number near the critical
+ *                        mass.  A different Markov chain than the reference's: dH is not comparable trajectory by
+ *                        trajectory, plaquette and acceptance agree statistically.  Single tile, even Nx and Nt. */
+enum { SM_SOLVER_REFERENCE = 0, SM_SOLVER_MIXED = 1, SM_SOLVER_CHRONO = 2, SM_SOLVER_EVENODD = 3 };
 SM_API int sm_set_solver(sm_ctx* ctx, int solver);
 /* device time (ms) of the last sm_* call on this context, measured with CUDA events on the
  * context's stream around the kernels only (no copies) */
@@ -125,6 +135,11 @@ SM_API int sm_conjugate_gradient(sm_ctx* ctx, const double* h_U0, const double* 
                           const double* h_phi1, double* h_x0, double* h_x1, double m0, int* converged,
                           int* iterations);
 /* phi_dag_partialD_phi  src/dirac_operator.cpp:486-580 (include/dirac_operator.h:93) */
+/* x_e = (Dhat Dhat^dagger)^-1 phi_e on the even sites (phi's odd sites are ignored, x's are zero): the solve of the
+ * opt-in even-odd HMC (SM_SOLVER_EVENODD), with the reference CG's start vector and stopping rule
+ * (src/conjugate_gradient.cpp:16,45) on the Schur complement of D */
+SM_API int sm_evenodd_solve(sm_ctx* ctx, const double* h_U0, const double* h_U1, const double* h_phi0, const double* h_phi1,
+                            double* h_x0, double* h_x1, double m0, int* converged, int* iterations);
 SM_API int sm_phi_dag_partialD_phi(sm_ctx* ctx, const double* h_U0, const double* h_U1, const double* h_left0,
                             const double* h_left1, const double* h_right0, const double* h_right1, double* h_F0,
                             double* h_F1);

@@ -17,7 +17,7 @@ HEADER_PATH = os.path.join(ROOT, "include", "schwinger_b200.h")
 SM_OK, SM_ERR_ARG, SM_ERR_CUDA, SM_ERR_NCCL, SM_ERR_IO, SM_ERR_STATE = range(6)
 SM_NCCL_ID_BYTES = 128
 SM_P2P_HANDLE_BYTES = 64
-SM_SOLVER_REFERENCE, SM_SOLVER_MIXED = 0, 1
+SM_SOLVER_REFERENCE, SM_SOLVER_MIXED, SM_SOLVER_CHRONO, SM_SOLVER_EVENODD = 0, 1, 2, 3
 
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int)
@@ -71,6 +71,7 @@ _SIGS = {
     "sm_D_D_dagger_phi": [ctx_p, dp, dp, dp, dp, dp, dp, C.c_double],
     "sm_dot": [ctx_p, dp, dp, dp, dp, dp],
     "sm_conjugate_gradient": [ctx_p, dp, dp, dp, dp, dp, dp, C.c_double, ip, ip],
+    "sm_evenodd_solve": [ctx_p, dp, dp, dp, dp, dp, dp, C.c_double, ip, ip],
     "sm_phi_dag_partialD_phi": [ctx_p, dp, dp, dp, dp, dp, dp, dp, dp],
     "sm_compute_staple": [ctx_p, dp, dp, dp, dp],
     "sm_compute_plaquette": [ctx_p, dp, dp, C.c_double, dp, dp],

@@ -236,6 +236,9 @@ int sm_destroy(sm_ctx* c) {
     if (c->win) cudaFree(c->win);
     if (c->push_ticket) cudaFree(c->push_ticket);
     if (c->comm) g_nccl.CommDestroy(c->comm);
+    if (c->eo_t) cudaFree(c->eo_t);
+    if (c->chrono_prev) cudaFree(c->chrono_prev);
+    if (c->chrono_guess) cudaFree(c->chrono_guess);
     void* ptrs[] = {c->partials, c->tickets, c->cg,      c->sums,    c->sums_loc, c->tmp,     c->cg_r,   c->cg_d,
                     c->cg_Ad,    c->cg_d2, c->sU,      c->sA,      c->sB,      c->sC,       c->sF,      c->U,      c->Up,
                     c->chi,      c->phi,     c->psi,     c->xi,      c->pi,       c->pip,     c->F,      c->send_tm,
@@ -289,7 +292,10 @@ int sm_set_cg(sm_ctx* c, double tol, int max_iter) {
 
 int sm_set_solver(sm_ctx* c, int solver) {
     NEED(c);
-    if (solver != SM_SOLVER_REFERENCE && solver != SM_SOLVER_MIXED) return fail(SM_ERR_ARG, "unknown solver");
+    if (solver != SM_SOLVER_REFERENCE && solver != SM_SOLVER_MIXED && solver != SM_SOLVER_CHRONO && solver != SM_SOLVER_EVENODD)
+        return fail(SM_ERR_ARG, "unknown solver");
+    if (solver == SM_SOLVER_EVENODD && (c->dist() || (c->Nx & 1) || (c->Nt & 1)))
+        return fail(SM_ERR_ARG, "the even-odd solver needs a single tile with even Nx and Nt");
     c->solver = solver;
     return SM_OK;
 }
@@ -434,6 +440,24 @@ int sm_conjugate_gradient(sm_ctx* c, const double* U0, const double* U1, const d
     TRY(h2d_c(c, c->sA, p0, p1));
     tick(c);
     TRY(dev_cg(c, c->sU, c->sA, c->sB, m0, converged, iterations));
+    TRY(tock(c));
+    TRY(d2h_c(c, c->sB, x0, x1));
+    return sync(c);
+}
+
+int sm_evenodd_solve(sm_ctx* c, const double* U0, const double* U1, const double* p0, const double* p1, double* x0,
+                     double* x1, double m0, int* converged, int* iterations) {
+    TRY(set_device(c));
+    NEED(U0); NEED(U1); NEED(p0); NEED(p1); NEED(x0); NEED(x1);
+    if (c->dist() || (c->Nx & 1) || (c->Nt & 1)) return fail(SM_ERR_ARG, "the even-odd solver needs a single tile with even Nx and Nt");
+    TRY(ensure_staging(c));
+    TRY(h2d_c(c, c->sU, U0, U1));
+    TRY(h2d_c(c, c->sA, p0, p1));
+    k_mask_parity<<<c->flat_blocks_s, kBlock, 0, c->stream>>>(c->sA, c->wt, c->V, 0);
+    KCHECK();
+    c->launches++;
+    tick(c);
+    TRY(dev_cg_eo(c, c->sU, c->sA, c->sB, m0, converged, iterations));
     TRY(tock(c));
     TRY(d2h_c(c, c->sB, x0, x1));
     return sync(c);
@@ -656,7 +680,7 @@ int sm_hmc_trajectory(sm_ctx* c, sm_traj_result* out) {
     if (c->hp.md_steps < 1) return fail(SM_ERR_STATE, "sm_hmc_configure first");
     TrajAcc acc;
     CU(cudaEventRecord(c->ev_t0, c->stream));
-    TRY(dev_D(c, c->U, c->chi, c->phi, c->hp.m0, false));                 // hmc.cpp:160
+    TRY(hmc_pseudofermion(c));                                            // hmc.cpp:160
     TRY(hmc_leapfrog(c, &acc));                                           // hmc.cpp:161
     TRY(hmc_hamiltonian_async(c, c->Up, c->pip, c->phi, 0, &acc));        // hmc.cpp:162 (new)
     TRY(hmc_hamiltonian_async(c, c->U, c->pi, c->phi, 5, &acc));          //             (old)
@@ -698,6 +722,7 @@ int sm_hmc_force(sm_ctx* c, const double* p0, const double* p1, double* F0, doub
     NEED(p0); NEED(p1); NEED(F0); NEED(F1);
     if (!c->hmc_has_gauge) return fail(SM_ERR_STATE, "sm_hmc_set_gauge first");
     TRY(h2d_c(c, c->phi, p0, p1));
+    TRY(hmc_adopt_phi(c));
     TrajAcc acc;
     tick(c);
     TRY(hmc_force(c, c->U, c->phi, c->F, &acc));
@@ -713,6 +738,7 @@ int sm_hmc_hamiltonian(sm_ctx* c, const double* pi0, const double* pi1, const do
     if (!c->hmc_has_gauge) return fail(SM_ERR_STATE, "sm_hmc_set_gauge first");
     TRY(h2d_r(c, c->pi, pi0, pi1));
     TRY(h2d_c(c, c->phi, p0, p1));
+    TRY(hmc_adopt_phi(c));
     tick(c);
     TRY(hmc_hamiltonian_async(c, c->U, c->pi, c->phi, 0, nullptr));
     TRY(tock(c));
@@ -728,6 +754,7 @@ int sm_hmc_leapfrog(sm_ctx* c, const double* pi0, const double* pi1, const doubl
     if (!c->hmc_has_gauge) return fail(SM_ERR_STATE, "sm_hmc_set_gauge first");
     TRY(h2d_r(c, c->pi, pi0, pi1));
     TRY(h2d_c(c, c->phi, p0, p1));
+    TRY(hmc_adopt_phi(c));
     TrajAcc acc;
     tick(c);
     TRY(hmc_leapfrog(c, &acc));

@@ -21,8 +21,8 @@ static int dev_cg_twopass(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, do
 
     k_cg_reset<<<1, 1, 0, c->stream>>>(st, tol, max_iter);
     c->launches++;
-    // Ad = DD^dagger phi ; r = phi - Ad ; d = r ; x = phi ; |phi|^2, |r|^2
-    TRY((launch_wilson<true, WILSON_PLAIN>(c, U, phi, c->tmp, m0)));
+    // Ad = DD^dagger x_0 ; r = phi - Ad ; d = r ; x = x_0 (= phi unless a start vector was given) ; |phi|^2, |r|^2
+    TRY((launch_wilson<true, WILSON_PLAIN>(c, U, c->cg_x0 ? c->cg_x0 : phi, c->tmp, m0)));
     TRY((launch_wilson<false, WILSON_CGINIT>(c, U, c->tmp, nullptr, m0, phi, c->cg_r, c->cg_d, x,
                                              sum_target(c, &st->phi_norm2))));
     TRY(sum_finish(c, &st->phi_norm2, 2));
@@ -190,14 +190,16 @@ static int dev_cg_fused(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, doub
     const unsigned int epoch_base = (++c->solve_seq) << 16;     // max_iter <= 10000 per solve (sm_set_cg caps it below 2^16)
     k_cg_reset<<<1, 1, 0, c->stream>>>(st, c->tol, c->max_iter, epoch_base);
     c->launches++;
-    // x = phi ; r = phi - D D^dagger phi ; |phi|^2, |r|^2   (d_0 = r_0 is formed by the first pass)
-    TRY((launch_wilson<true, WILSON_PLAIN>(c, U, phi, c->tmp, m0)));
+    // x = x_0 (phi unless a start vector was given) ; r = phi - D D^dagger x_0 ; |phi|^2, |r|^2   (d_0 = r_0 is formed by the first pass)
+    TRY((launch_wilson<true, WILSON_PLAIN>(c, U, c->cg_x0 ? c->cg_x0 : phi, c->tmp, m0)));
     TRY((launch_wilson<false, WILSON_CGINIT>(c, U, c->tmp, nullptr, m0, phi, c->cg_r, c->cg_d2, x,
                                              sum_target(c, &st->phi_norm2))));
     TRY(sum_finish(c, &st->phi_norm2, 2));
     // peer-memory halos: r_0's boundary rows into the neighbours' ghosts (parity 0, epoch base + 0); later r_k are
     // stored by k_cg_resid_dist itself
     if (c->peer_sums) TRY(p2p_push(c, c->cg_r, 1, c->stream, (long long)epoch_base, 0));
+    // (Measured and dropped: keeping A d -- or A d and a copy of U -- in the persisting part of L2 with an access-policy
+    // window made the 1024^2 solve slower, 63.7 -> 92 us per iteration; profiles/r02_cg_1024_l2_persistence.txt.)
     TRY(cg_fused_loop<cplx>(c, U, c->cg_r, x, c->cg_d, c->cg_d2, c->cg_Ad, m0, c->max_iter));
     if (converged) *converged = c->h->cg[0].converged;
     if (iterations) *iterations = c->h->cg[0].iters;
@@ -268,6 +270,7 @@ static int resident_args(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, dou
     a->U = U;
     a->phi = phi;
     a->x = x;
+    a->x0 = c->cg_x0;
     a->wx = c->wx;
     a->wt = c->wt;
     a->V = c->V;
@@ -443,7 +446,71 @@ static int dev_cg_cols(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, doubl
     return resident_finish(c, converged, iterations);
 }
 
-static int dev_cg(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, int* converged, int* iterations) {
+// Opt-in even-odd solver: CG for  Dhat Dhat^dagger x = phi  on the even sites, Dhat the Schur complement of
+// D (sm_ops.cuh: dev_Dhat).  Same recurrences, start vector (x_0 = phi) and stopping rule as the reference's CG
+// (src/conjugate_gradient.cpp:4-67), another operator: its condition number is ~4x smaller near the critical mass
+// (lambda_hat = lambda_+ lambda_- / m), so the solve takes a fraction of the iterations.  phi, x: full-lattice arrays,
+// zero on the odd sites.  Iterations are launched in batches; the host polls the device scalars one batch behind.
+static int dev_cg_eo(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, int* converged, int* iterations) {
+    TRY(ensure_complex(c, &c->tmp));
+    TRY(ensure_complex(c, &c->eo_t));
+    TRY(ensure_complex(c, &c->cg_r));
+    TRY(ensure_complex(c, &c->cg_d));
+    TRY(ensure_complex(c, &c->cg_Ad));
+    const int n_elems = 2 * c->V;
+    const double tol = c->tol;
+    const int max_iter = c->max_iter;
+    CgState* st = c->cg;
+    const int* done = &st->done;
+    k_cg_reset<<<1, 1, 0, c->stream>>>(st, tol, max_iter);
+    c->launches++;
+    // A phi, then x = phi ; r = phi - A phi ; d = r ; |phi|^2, |r|^2
+    TRY((dev_Dhat<true>(c, U, phi, c->tmp, c->eo_t, m0)));
+    TRY((dev_Dhat<false>(c, U, c->eo_t, c->tmp, c->cg_Ad, m0)));
+    k_cg_start<<<c->flat_blocks_c, kBlock, 0, c->stream>>>(phi, c->cg_Ad, x, c->cg_r, c->cg_d, n_elems, c->partials,
+                                                           c->tickets + TK_DOT, &st->phi_norm2);
+    KCHECK();
+    c->launches++;
+    const int batch = 8;
+    int k = 0, slot = 0, prev = -1;
+    for (;;) {
+        const int k_end = std::min(max_iter, k + batch);
+        for (; k < k_end; k++) {
+            const int cur = k & 1;
+            if (k > 0) {
+                k_cg_dir<<<c->flat_blocks_c, kBlock, 0, c->stream>>>(st, k, tol, c->cg_r, c->cg_d, n_elems);
+                KCHECK();
+                c->launches++;
+            }
+            TRY((dev_Dhat<true>(c, U, c->cg_d, c->tmp, c->eo_t, m0, nullptr, nullptr, done)));
+            TRY((dev_Dhat<false>(c, U, c->eo_t, c->tmp, c->cg_Ad, m0, c->cg_d, st->dAd, done)));
+            k_cg_update<<<c->flat_blocks_c, kBlock, 0, c->stream>>>(st, cur, x, c->cg_d, c->cg_r, c->cg_Ad, n_elems,
+                                                                    c->partials, c->tickets + TK_UPDATE, &st->rr[cur ^ 1]);
+            KCHECK();
+            c->launches++;
+        }
+        k_cg_check<<<1, 1, 0, c->stream>>>(st, k, tol, max_iter);
+        KCHECK();
+        c->launches++;
+        CU(cudaMemcpyAsync(&c->h->cg[slot], st, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaEventRecord(c->ev_poll[slot], c->stream));
+        if (prev >= 0) {
+            CU(cudaEventSynchronize(c->ev_poll[prev]));
+            if (c->h->cg[prev].done) break;
+        }
+        if (k >= max_iter) break;
+        prev = slot;
+        slot ^= 1;
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpyAsync(&c->h->cg[0], st, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (converged) *converged = c->h->cg[0].converged;
+    if (iterations) *iterations = c->h->cg[0].iters;
+    return SM_OK;
+}
+
+static int dev_cg_route(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, int* converged, int* iterations) {
     if (c->use_cluster && !c->dist()) {
         if (cols_plan(c) >= 0) return dev_cg_cols(c, U, phi, x, m0, converged, iterations);
         if (c->V <= kClusterMaxCtas * kClusterThreads && cluster_ok(c)) return dev_cg_cluster(c, U, phi, x, m0, converged, iterations);
@@ -452,4 +519,14 @@ static int dev_cg(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0,
     if (c->solver == SM_SOLVER_MIXED && fused_ok(c) && !c->dist()) return dev_cg_mixed(c, U, phi, x, m0, converged, iterations);
     if (fused_ok(c)) return dev_cg_fused(c, U, phi, x, m0, converged, iterations);
     return dev_cg_twopass(c, U, phi, x, m0, converged, iterations);
+}
+
+// x0: start vector (null: x_0 = phi, the reference's choice, src/conjugate_gradient.cpp:16).  Everything else -- the
+// recurrences, the stopping rule |r| < tol |phi| -- is the same; only the opt-in chronological solver passes one.
+static int dev_cg(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, int* converged, int* iterations,
+                  const cplx* x0 = nullptr) {
+    c->cg_x0 = (c->solver == SM_SOLVER_MIXED) ? nullptr : x0;
+    const int rc = dev_cg_route(c, U, phi, x, m0, converged, iterations);
+    c->cg_x0 = nullptr;
+    return rc;
 }

@@ -36,6 +36,7 @@ struct ResidentCgArgs {
     const cplx* U;
     const cplx* phi;
     cplx* x;
+    const cplx* x0;     // start vector (opt-in chronological guess); null: x_0 = phi as the reference (conjugate_gradient.cpp:16)
     int wx, wt, V;
     double mass;
     double sR_edge, sL_edge;
@@ -279,11 +280,16 @@ __device__ __forceinline__ void resident_cg(const ResidentCgArgs& a, Comm& comm)
     // Buffer 0 carries the halves of psi / r, buffer 1 those of t; a buffer (and a sum slot) is rewritten
     // only after a later barrier than the one its readers waited on.
 
-    // x = phi ; r = phi - D D^dagger phi ; d = r   (conjugate_gradient.cpp:16-24).
+    // x = phi (or the caller's start vector) ; r = phi - D D^dagger x ; d = r   (conjugate_gradient.cpp:16-24).
+    cplx g0 = f0, g1 = f1;
+    if (a.x0 != nullptr && active) {
+        g0 = a.x0[n];
+        g1 = a.x0[V + n];
+    }
     cplx r0, r1, d0, d1, A0, A1, t0, t1;
-    publish(Hop<true>{}, 0, f0, f1);
+    publish(Hop<true>{}, 0, g0, g1);
     comm.barrier();
-    combine(Hop<true>{}, fetch(0), f0, f1, t0, t1);
+    combine(Hop<true>{}, fetch(0), g0, g1, t0, t1);
     publish(Hop<false>{}, 1, t0, t1);
     comm.barrier();
     combine(Hop<false>{}, fetch(1), t0, t1, A0, A1);
@@ -292,10 +298,10 @@ __device__ __forceinline__ void resident_cg(const ResidentCgArgs& a, Comm& comm)
     if (!active) r0 = r1 = zero;
     d0 = r0;
     d1 = r1;
-    cplx xr0 = f0, xr1 = f1;                            // x when it is kept in registers
+    cplx xr0 = g0, xr1 = g1;                            // x when it is kept in registers
     if (!Comm::kXInRegisters && active) {               // else x lives in L2: only ever updated in place
-        a.x[n] = f0;
-        a.x[V + n] = f1;
+        a.x[n] = g0;
+        a.x[V + n] = g1;
     }
     double s2[2] = {f0.x * f0.x + f0.y * f0.y + f1.x * f1.x + f1.y * f1.y,
                     r0.x * r0.x + r0.y * r0.y + r1.x * r1.x + r1.y * r1.y};

@@ -193,8 +193,8 @@ __global__ void __launch_bounds__(T, 1) k_cg_cols(const ResidentCgArgs a) {
             const double sg = (t == wt - 1) ? -0.5 * a.sR_edge : -0.5;   // the host checks sR_edge == sL_edge (one tile)
             u0 = cscale(sg, a.U[n]);
             u1 = cscale(-0.5, a.U[Vs + n]);
-            f0 = a.phi[n];
-            f1 = a.phi[Vs + n];
+            f0 = a.x0 ? a.x0[n] : a.phi[n];      // start vector: phi as the reference, or the caller's guess
+            f1 = a.x0 ? a.x0[Vs + n] : a.phi[Vs + n];
         }
         su[(0 * S + j) * T + tid] = u0;
         su[(1 * S + j) * T + tid] = u1;
@@ -212,7 +212,14 @@ __global__ void __launch_bounds__(T, 1) k_cg_cols(const ResidentCgArgs a) {
     double s2[2] = {0.0, 0.0};
 #pragma unroll
     for (int j = 0; j < S; j++) {
-        const cplx f0 = sx[(0 * S + j) * T + tid], f1 = sx[(1 * S + j) * T + tid];
+        cplx f0 = sx[(0 * S + j) * T + tid], f1 = sx[(1 * S + j) * T + tid];
+        if (a.x0 != nullptr) {                                     // x_0 != phi: fetch phi again for r_0 and |phi|
+            f0 = f1 = zero;
+            if (j < nslots) {
+                f0 = a.phi[nb + j * wt];
+                f1 = a.phi[Vs + nb + j * wt];
+            }
+        }
         const cplx r0 = csub(f0, w0[j]), r1 = csub(f1, w1[j]);    // zero in an empty slot
         sr[(0 * S + j) * T + tid] = r0;
         sr[(1 * S + j) * T + tid] = r1;

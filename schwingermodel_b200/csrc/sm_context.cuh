@@ -137,6 +137,7 @@ struct sm_ctx {
 
     // work fields (2V complex each)
     cplx *tmp = nullptr, *cg_r = nullptr, *cg_d = nullptr, *cg_Ad = nullptr, *cg_d2 = nullptr;
+    cplx* eo_t = nullptr;   // even-odd solver: Dhat^dagger d
     // staging for the host-buffer API
     cplx *sU = nullptr, *sA = nullptr, *sB = nullptr, *sC = nullptr;
     double* sF = nullptr;
@@ -187,6 +188,9 @@ struct sm_ctx {
     bool use_graphs = true;
     unsigned int attr_done = 0;   // kernel attributes already set on this context's device
     int solver = SM_SOLVER_REFERENCE;
+    const cplx* cg_x0 = nullptr;      // start vector of the running solve (null: phi, as the reference)
+    cplx *chrono_prev = nullptr, *chrono_guess = nullptr;   // SM_SOLVER_CHRONO: previous Force solution, extrapolated guess
+    int chrono_have = 0;              // solutions of this trajectory's Force solves kept so far (0, 1, 2)
     cplxf *mx_U = nullptr, *mx_r = nullptr, *mx_e = nullptr, *mx_d0 = nullptr, *mx_d1 = nullptr, *mx_Ad = nullptr;
     bool use_cluster = true;   // whole-solve resident kernels for small lattices (SM_CLUSTER_CG=0 disables)
     int coop_sites = -1;

@@ -131,12 +131,13 @@ __device__ __forceinline__ void fused_cg_wait_ghosts(const FusedArgsT<C>& a) {
     }
 }
 
-// the finishing block of a FUSED_DOT / FUSED_CG pass files dot(d, A d): CgState (or the caller's buffer), or the ranks' slots
+// the finishing block of a FUSED_DOT / FUSED_CG pass files dot(d, A d): CgState (or the caller's buffer), or the ranks'
+// slots.  Called by warp 0 of that block (the sums are valid in lane 0).
 template <typename C>
 __device__ __forceinline__ void fused_sums_out(const FusedArgsT<C>& a, const double (&acc)[2]) {
     if (a.dl.on) {
         publish_sums<2>(a.dl, 0, a.cur, a.st->epoch_base + (unsigned int)a.st->k + 1u, acc);
-    } else {
+    } else if ((threadIdx.x & 31) == 0) {
         a.sums_out[0] = acc[0];
         a.sums_out[1] = acc[1];
     }
@@ -373,7 +374,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_fused(const FusedArgsT<C> a) {
 
     if (MODE != FUSED_PLAIN) {
         if (grid_reduce<2>(acc, a.partials, a.ticket, (int)gridDim.x * a.nchunks, chunk * (int)gridDim.x + (int)blockIdx.x)) {
-            if (tid == 0) fused_sums_out(a, acc);
+            if (tid < 32) fused_sums_out(a, acc);
         }
     }
 }
@@ -450,17 +451,19 @@ __global__ void __launch_bounds__(kBlock) k_cg_resid_dist(CgState* st, int cur, 
         acc[0] += rv.x * rv.x + rv.y * rv.y;
     }
     if (grid_reduce<1>(acc, partials, ticket, -1, -1, true)) {
-        if (threadIdx.x == 0) {
-            const unsigned int e = st->epoch_base + (unsigned int)st->k + 1u;
-            st->alpha[0] = alpha.x;
-            st->alpha[1] = alpha.y;
-            st->pending = 1;
-            st->pending_buf = cur;
-            st->k = st->k + 1;
-            publish_sums<1>(dl, 1, cur, e, acc);
-            __threadfence_system();
-            st_release_sys(dl.flag_xm, e);
-            st_release_sys(dl.flag_xp, e);
+        if (threadIdx.x < 32) {
+            const unsigned int e = st->epoch_base + (unsigned int)st->k + 1u;   // every lane reads k before lane 0 bumps it
+            __syncwarp();
+            if (threadIdx.x == 0) {
+                st->alpha[0] = alpha.x;
+                st->alpha[1] = alpha.y;
+                st->pending = 1;
+                st->pending_buf = cur;
+                st->k = st->k + 1;
+            }
+            // |r|^2 to every rank's slot and the neighbours' ghost flags, behind one system-scope fence (every block
+            // fenced its own peer stores before it took its ticket)
+            publish_sums<1>(dl, 1, cur, e, acc, dl.flag_xm, dl.flag_xp);
         }
     }
 }

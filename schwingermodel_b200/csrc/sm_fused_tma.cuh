@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_tma(const FusedArgsT<cplx> a) 
 
     if (MODE != FUSED_PLAIN) {
         if (grid_reduce<2>(acc, a.partials, a.ticket, (int)gridDim.x * a.nchunks, chunk * (int)gridDim.x + (int)blockIdx.x)) {
-            if (tid == 0) fused_sums_out(a, acc);
+            if (tid < 32) fused_sums_out(a, acc);
         }
     }
 }

@@ -237,10 +237,60 @@ static int hmc_alloc(sm_ctx* c) {
     return SM_OK;
 }
 
-// HMC::Force (hmc.cpp:44-60): psi = (DD^dagger)^-1 phi ; chi' = D^dagger psi ; fermion + gauge force
-static int hmc_force(sm_ctx* c, const cplx* U, const cplx* phi, double* F, TrajAcc* acc) {
+// HMC::Force (hmc.cpp:44-60): psi = (DD^dagger)^-1 phi ; chi' = D^dagger psi ; fermion + gauge force.
+// Opt-in SM_SOLVER_CHRONO: the solve starts from the solution of the previous force evaluation of the
+// trajectory (second one) or from the linear extrapolation 2 psi_{-1} - psi_{-2} of the last two (later ones) instead
+// of from phi; the CG itself and its stopping rule are unchanged.
+// Opt-in even-odd HMC (SM_SOLVER_EVENODD): the pseudofermion lives on the even sites and its action is
+//   S_pf = phi_e^dagger (Dhat Dhat^dagger)^-1 phi_e,   Dhat = m - (1/4m) H_eo H_oe  the Schur complement of D,
+// which has the same determinant as D D^dagger up to a constant (det D = m^{V/2} det Dhat), i.e. the same distribution of
+// gauge fields.  With X_e = (Dhat Dhat^dagger)^-1 phi_e and Y_e = Dhat^dagger X_e the variation is
+//   dS = -2 Re( X^dagger dD Y )  on the full lattice with  X_o = -(1/m) (D^dagger X_e)_o ,  Y_o = -(1/m) (D Y_e)_o ,
+// so the force is the reference's bilinear phi_dag_partialD_phi(U, X, Y) (src/dirac_operator.cpp:486-580) of the
+// completed fields, plus the unchanged gauge force.
+static int hmc_force_eo(sm_ctx* c, const cplx* U, const cplx* phi, double* F, TrajAcc* acc) {
     int ok = 0, its = 0;
-    TRY(dev_cg(c, U, phi, c->psi, c->hp.m0, &ok, &its));
+    const double m0 = c->hp.m0, m = m0 + 2;
+    TRY(dev_cg_eo(c, U, phi, c->psi, m0, &ok, &its));
+    if (acc) {
+        acc->dd_apps += ok ? its + 2 : its + 1;
+        acc->solves++;
+        acc->all_ok &= ok;
+        acc->force_fail += ok ? 0 : 1;
+    }
+    TRY((dev_Dhat<true>(c, U, c->psi, c->tmp, c->xi, m0)));                                           // Y_e
+    TRY((launch_wilson_eo<true, WILSON_EO>(c, U, c->psi, c->tmp, m0, 1, nullptr, 0.0, -1.0 / m)));     // X_o
+    k_add_into<<<c->flat_blocks_c, kBlock, 0, c->stream>>>(c->psi, c->tmp, 2 * c->V);
+    KCHECK();
+    TRY((launch_wilson_eo<false, WILSON_EO>(c, U, c->xi, c->tmp, m0, 1, nullptr, 0.0, -1.0 / m)));    // Y_o
+    k_add_into<<<c->flat_blocks_c, kBlock, 0, c->stream>>>(c->xi, c->tmp, 2 * c->V);
+    KCHECK();
+    c->launches += 2;
+    return dev_force(c, U, c->psi, c->xi, F, c->hp.beta, true, true);
+}
+
+static int hmc_force(sm_ctx* c, const cplx* U, const cplx* phi, double* F, TrajAcc* acc) {
+    if (c->solver == SM_SOLVER_EVENODD) return hmc_force_eo(c, U, phi, F, acc);
+    int ok = 0, its = 0;
+    const cplx* x0 = nullptr;
+    if (c->solver == SM_SOLVER_CHRONO && c->chrono_have > 0) {
+        TRY(ensure_complex(c, &c->chrono_guess));
+        if (c->chrono_have >= 2) {
+            k_extrapolate<<<c->flat_blocks_c, kBlock, 0, c->stream>>>(c->psi, c->chrono_prev, c->chrono_guess, 2 * c->V);
+            KCHECK();
+            c->launches++;
+        } else {
+            CU(cudaMemcpyAsync(c->chrono_guess, c->psi, sizeof(cplx) * 2 * c->V, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        x0 = c->chrono_guess;
+    }
+    if (c->solver == SM_SOLVER_CHRONO) {          // psi is about to be overwritten: keep it as psi_{-2} of the next solve
+        TRY(ensure_complex(c, &c->chrono_prev));
+        if (c->chrono_have > 0)
+            CU(cudaMemcpyAsync(c->chrono_prev, c->psi, sizeof(cplx) * 2 * c->V, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    TRY(dev_cg(c, U, phi, c->psi, c->hp.m0, &ok, &its, x0));
+    if (c->solver == SM_SOLVER_CHRONO) c->chrono_have = std::min(2, c->chrono_have + 1);
     if (acc) {
         acc->dd_apps += ok ? its + 2 : its + 1;
         acc->solves++;
@@ -251,6 +301,25 @@ static int hmc_force(sm_ctx* c, const cplx* U, const cplx* phi, double* F, TrajA
     return dev_force(c, U, c->psi, c->xi, F, c->hp.beta, true, true);
 }
 
+// phi = D chi (hmc.cpp:160); even-odd HMC: phi_e = Dhat chi_e, chi's odd sites dropped
+static int hmc_pseudofermion(sm_ctx* c) {
+    if (c->solver != SM_SOLVER_EVENODD) return dev_D(c, c->U, c->chi, c->phi, c->hp.m0, false);
+    TRY(ensure_complex(c, &c->tmp));
+    k_mask_parity<<<c->flat_blocks_s, kBlock, 0, c->stream>>>(c->chi, c->wt, c->V, 0);
+    KCHECK();
+    c->launches++;
+    return dev_Dhat<false>(c, c->U, c->chi, c->tmp, c->phi, c->hp.m0);
+}
+
+// a pseudofermion supplied by the caller (test entry points): the even-odd action sees its even sites only
+static int hmc_adopt_phi(sm_ctx* c) {
+    if (c->solver != SM_SOLVER_EVENODD) return SM_OK;
+    k_mask_parity<<<c->flat_blocks_s, kBlock, 0, c->stream>>>(c->phi, c->wt, c->V, 0);
+    KCHECK();
+    c->launches++;
+    return SM_OK;
+}
+
 // HMC::Leapfrog (hmc.cpp:63-103): position first, MD_steps-1 force evaluations
 static int hmc_leapfrog(sm_ctx* c, TrajAcc* acc) {
     const int md = c->hp.md_steps;
@@ -258,6 +327,7 @@ static int hmc_leapfrog(sm_ctx* c, TrajAcc* acc) {
     CU(cudaMemcpyAsync(c->pip, c->pi, sizeof(double) * 2 * c->V, cudaMemcpyDeviceToDevice, c->stream));
     CU(cudaMemcpyAsync(c->Up, c->U, sizeof(cplx) * 2 * c->V, cudaMemcpyDeviceToDevice, c->stream));
     invalidate_gauge_ghosts(c, c->Up);
+    c->chrono_have = 0;     // a new trajectory: U' jumps back to U, earlier solutions are no guide
     TRY(dev_leap_update(c, c->Up, c->pip, nullptr, 0.0, 0.5 * eps));
     TRY(hmc_force(c, c->Up, c->phi, c->F, acc));
     for (int step = 1; step < md - 1; step++) {
@@ -273,7 +343,10 @@ static int hmc_hamiltonian_async(sm_ctx* c, const cplx* U, const double* pi, con
     TRY(dev_kinetic(c, pi, c->sums + base));
     TRY(dev_plaquette(c, U, c->hp.beta, nullptr, c->sums + base + 1));
     int ok = 0, its = 0;
-    TRY(dev_cg(c, U, phi, c->xi, c->hp.m0, &ok, &its));
+    // opt-in chronological start: the proposal's action solve sits half a link step after the last force solve
+    const cplx* x0 = (c->solver == SM_SOLVER_CHRONO && c->chrono_have > 0 && U == c->Up) ? c->psi : nullptr;
+    if (c->solver == SM_SOLVER_EVENODD) TRY(dev_cg_eo(c, U, phi, c->xi, c->hp.m0, &ok, &its));   // phi lives on the even sites
+    else TRY(dev_cg(c, U, phi, c->xi, c->hp.m0, &ok, &its, x0));
     if (acc) {
         acc->dd_apps += ok ? its + 2 : its + 1;
         acc->solves++;

@@ -83,13 +83,17 @@ struct CgState {
 // same quantities the reference ships in TopRow/BottomRow/LeftCol/RightCol
 // (src/dirac_operator.cpp:49-64); a null ghost pointer means "wrap locally".
 // ----------------------------------------------------------------------------------------------
-enum { WILSON_PLAIN = 0, WILSON_DOT = 1, WILSON_CGINIT = 2 };
+// WILSON_EO / WILSON_EO_DOT: building blocks of the even-odd (Schur complement) operator of the opt-in even-odd HMC,
+// on full-lattice arrays that are zero on one parity:  out(n) = [parity(n) == eo_keep] (eo_self aux(n) + eo_hop (D in)(n)),
+// zero elsewhere (sites of the other parity are not computed); _DOT adds the partial of dot(aux2, out).
+enum { WILSON_PLAIN = 0, WILSON_DOT = 1, WILSON_CGINIT = 2, WILSON_EO = 3, WILSON_EO_DOT = 4 };
 
 struct WilsonArgs {
     const cplx* U;
     const cplx* in;
     cplx* out;
     const cplx* aux;   // DOT: d ; CGINIT: phi
+    const cplx* aux2;  // CGINIT: the start vector x_0 when it is not phi (opt-in chronological guess), else null
     cplx* r;           // CGINIT outputs
     cplx* d;
     cplx* x;
@@ -106,6 +110,8 @@ struct WilsonArgs {
     unsigned int* ticket;
     double* sums_out;
     const int* done;   // CG early-out flag (null outside CG)
+    int eo_keep;           // EO modes: parity (x + t) & 1 of the sites that are computed
+    double eo_self, eo_hop;
     int interior_only;     // split lattice with overlap: skip the sites that read ghost lines ...
     int boundary_blocks;   // ... k_wilson_boundary (this many blocks) computes them and joins the reduction
     int interior_blocks;   // (boundary launch) blocks of the interior launch
@@ -196,6 +202,21 @@ __device__ __forceinline__ void wilson_epilogue(const WilsonArgs& a, int n, cplx
     if (MODE == WILSON_PLAIN) {
         a.out[n] = o0;
         a.out[a.V + n] = o1;
+    } else if (MODE == WILSON_EO || MODE == WILSON_EO_DOT) {
+        cplx v0 = cscale(a.eo_hop, o0), v1 = cscale(a.eo_hop, o1);
+        if (a.aux != nullptr) {
+            const cplx s0 = ld_stream(a.aux + n), s1 = ld_stream(a.aux + a.V + n);
+            v0 = make_double2(fma(a.eo_self, s0.x, v0.x), fma(a.eo_self, s0.y, v0.y));
+            v1 = make_double2(fma(a.eo_self, s1.x, v1.x), fma(a.eo_self, s1.y, v1.y));
+        }
+        a.out[n] = v0;
+        a.out[a.V + n] = v1;
+        if (MODE == WILSON_EO_DOT) {
+            const cplx d0 = ld_stream(a.aux2 + n), d1 = ld_stream(a.aux2 + a.V + n);
+            const cplx p0 = cmul_conj(d0, v0), p1 = cmul_conj(d1, v1);
+            acc[0] += p0.x + p1.x;
+            acc[NS - 1] += p0.y + p1.y;
+        }
     } else if (MODE == WILSON_DOT) {
         // Ad = D t, partial of dot(d, Ad) = sum d conj(Ad)   (conjugate_gradient.cpp:32-33)
         a.out[n] = o0;
@@ -208,8 +229,13 @@ __device__ __forceinline__ void wilson_epilogue(const WilsonArgs& a, int n, cplx
         // x = phi ; r = phi - DD^dagger phi ; d = r   (conjugate_gradient.cpp:16-24)
         const cplx f0 = ld_stream(a.aux + n), f1 = ld_stream(a.aux + a.V + n);
         const cplx r0 = csub(f0, o0), r1 = csub(f1, o1);
-        a.x[n] = f0;
-        a.x[a.V + n] = f1;
+        if (a.aux2 != nullptr) {
+            a.x[n] = a.aux2[n];
+            a.x[a.V + n] = a.aux2[a.V + n];
+        } else {
+            a.x[n] = f0;
+            a.x[a.V + n] = f1;
+        }
         a.r[n] = r0;
         a.r[a.V + n] = r1;
         a.d[n] = r0;
@@ -231,7 +257,7 @@ __global__ void __launch_bounds__(kBlock) k_wilson(const WilsonArgs a) {
     const bool t_ok = t < a.wt;
     const int x_begin = blockIdx.y * a.rows_per_block;
     const int x_end = min(a.wx, x_begin + a.rows_per_block);
-    constexpr int NS = (MODE == WILSON_PLAIN) ? 1 : 2;
+    constexpr int NS = (MODE == WILSON_PLAIN || MODE == WILSON_EO) ? 1 : 2;
     double acc[NS];
 #pragma unroll
     for (int j = 0; j < NS; j++) acc[j] = 0.0;
@@ -239,12 +265,18 @@ __global__ void __launch_bounds__(kBlock) k_wilson(const WilsonArgs a) {
     if (t_ok) {
         for (int x = x_begin + threadIdx.y; x < x_end; x += blockDim.y) {
             if (a.interior_only && wilson_on_boundary(a, x, t)) continue;   // k_wilson_boundary takes those
+            if ((MODE == WILSON_EO || MODE == WILSON_EO_DOT) && ((x + t) & 1) != a.eo_keep) {   // the other parity: zero
+                const int n = x * a.wt + t;
+                a.out[n] = make_double2(0.0, 0.0);
+                a.out[a.V + n] = make_double2(0.0, 0.0);
+                continue;
+            }
             cplx o0, o1;
             wilson_site<DAG>(a, x, t, o0, o1);
             wilson_epilogue<MODE, NS>(a, x * a.wt + t, o0, o1, acc);
         }
     }
-    if (MODE != WILSON_PLAIN) {
+    if (MODE != WILSON_PLAIN && MODE != WILSON_EO) {
         const int nb = gridDim.x * gridDim.y;
         if (grid_reduce<NS>(acc, a.partials, a.ticket, nb + a.boundary_blocks, blockIdx.y * gridDim.x + blockIdx.x)) {
             if (threadIdx.x == 0 && threadIdx.y == 0) {
@@ -441,6 +473,58 @@ __global__ void k_cg_reset(CgState* st, double tol, int max_iter, unsigned int e
     st->pending = 0;
     st->pending_buf = 0;
     st->k = 0;
+}
+
+// CG start from a finished A phi (even-odd solver): x = phi ; r = phi - A phi ; d = r ; sums |phi|^2, |r|^2
+__global__ void __launch_bounds__(kBlock) k_cg_start(const cplx* __restrict__ phi, const cplx* __restrict__ Aphi,
+                                                     cplx* __restrict__ x, cplx* __restrict__ r, cplx* __restrict__ d,
+                                                     int n_elems, double* partials, unsigned int* ticket, double* sums_out) {
+    double acc[2] = {0.0, 0.0};
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += stride) {
+        const cplx f = ld_stream(phi + i), av = ld_stream(Aphi + i);
+        const cplx rv = csub(f, av);
+        x[i] = f;
+        r[i] = rv;
+        d[i] = rv;
+        acc[0] += f.x * f.x + f.y * f.y;
+        acc[1] += rv.x * rv.x + rv.y * rv.y;
+    }
+    if (grid_reduce<2>(acc, partials, ticket)) {
+        if (threadIdx.x == 0) {
+            sums_out[0] = acc[0];
+            sums_out[1] = acc[1];
+        }
+    }
+}
+
+// keep one parity of a field: f(n) = 0 where (x + t) & 1 != keep
+__global__ void __launch_bounds__(kBlock) k_mask_parity(cplx* __restrict__ f, int wt, int V, int keep) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < V; n += stride) {
+        const int x = n / wt, t = n - x * wt;
+        if (((x + t) & 1) != keep) {
+            f[n] = make_double2(0.0, 0.0);
+            f[V + n] = make_double2(0.0, 0.0);
+        }
+    }
+}
+
+// y += x
+__global__ void __launch_bounds__(kBlock) k_add_into(cplx* __restrict__ y, const cplx* __restrict__ x, int n_elems) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += stride) y[i] = cadd(y[i], ld_stream(x + i));
+}
+
+// chronological start vector (opt-in): g = 2 a - b, the linear extrapolation of the last two solutions along the
+// molecular-dynamics trajectory
+__global__ void __launch_bounds__(kBlock) k_extrapolate(const cplx* __restrict__ a, const cplx* __restrict__ b,
+                                                        cplx* __restrict__ g, int n_elems) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += stride) {
+        const cplx u = ld_stream(a + i), v = ld_stream(b + i);
+        g[i] = make_double2(2.0 * u.x - v.x, 2.0 * u.y - v.y);
+    }
 }
 
 // dot(x,y) = sum x conj(y) over both components (include/variables.h:181-192)

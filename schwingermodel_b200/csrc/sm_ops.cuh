@@ -29,6 +29,7 @@ static int launch_wilson(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, do
     a.in = in;
     a.out = out;
     a.aux = aux;
+    a.aux2 = (MODE == WILSON_CGINIT) ? c->cg_x0 : nullptr;
     a.r = r;
     a.d = d;
     a.x = x;
@@ -67,6 +68,51 @@ static int launch_wilson(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, do
         c->launches++;
     }
     return SM_OK;
+}
+
+// ---- even-odd building block (single tile): out = [parity == keep] (self aux + hop D in), see WILSON_EO ----------------
+template <bool DAG, int MODE>
+static int launch_wilson_eo(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, double m0, int keep, const cplx* aux,
+                            double self, double hop, const cplx* dot_with = nullptr, double* sums_out = nullptr,
+                            const int* done = nullptr) {
+    static_assert(MODE == WILSON_EO || MODE == WILSON_EO_DOT, "even-odd modes only");
+    if (c->dist()) return fail(SM_ERR_STATE, "the even-odd solver runs on a single tile");
+    WilsonArgs a{};
+    a.U = U;
+    a.in = in;
+    a.out = out;
+    a.aux = aux;
+    a.aux2 = dot_with;
+    a.wx = c->wx;
+    a.wt = c->wt;
+    a.V = c->V;
+    a.rows_per_block = c->rows_per_block;
+    a.mass = m0 + 2;
+    a.sR_edge = c->sR_edge();
+    a.sL_edge = c->sL_edge();
+    a.partials = c->partials;
+    a.ticket = c->tickets + TK_WILSON;
+    a.sums_out = sums_out;
+    a.done = done;
+    a.eo_keep = keep;
+    a.eo_self = self;
+    a.eo_hop = hop;
+    k_wilson<DAG, MODE><<<c->wil_grid, c->wil_block, 0, c->stream>>>(a);
+    KCHECK();
+    c->launches++;
+    return SM_OK;
+}
+
+// Schur complement of D on the even sites,  Dhat = m - (1/4m) H_eo H_oe  (m = m0 + 2, D = m - H/2), or its adjoint, applied
+// to a field that is zero on the odd sites:  W = [odd] D v ;  out = [even] (m v - (1/m) D W).  `dot_with`: also dot(dot_with, out).
+template <bool DAG>
+static int dev_Dhat(sm_ctx* c, const cplx* U, const cplx* v, cplx* W, cplx* out, double m0, const cplx* dot_with = nullptr,
+                    double* sums_out = nullptr, const int* done = nullptr) {
+    const double m = m0 + 2;
+    TRY((launch_wilson_eo<DAG, WILSON_EO>(c, U, v, W, m0, 1, nullptr, 0.0, 1.0, nullptr, nullptr, done)));
+    if (dot_with != nullptr)
+        return launch_wilson_eo<DAG, WILSON_EO_DOT>(c, U, W, out, m0, 0, v, m, -1.0 / m, dot_with, sums_out, done);
+    return launch_wilson_eo<DAG, WILSON_EO>(c, U, W, out, m0, 0, v, m, -1.0 / m, nullptr, nullptr, done);
 }
 
 static int dev_D(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, double m0, bool dagger) {

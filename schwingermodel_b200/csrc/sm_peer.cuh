@@ -68,16 +68,31 @@ __device__ __forceinline__ void spin_until(const unsigned int* flag, unsigned in
     }
 }
 
-// One thread: my partial sums -> slot (kind, parity, my rank) of every rank, released with `epoch`.
+__device__ __forceinline__ void st_relaxed_sys_u32(unsigned int* p, unsigned int v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Warp 0 of the finishing block (all 32 lanes; the sums are valid in lane 0): my partial sums -> slot (kind, parity,
+// my rank) of every rank, lane p serving rank p, then ONE system-scope fence for the warp, then the epochs.  (A
+// release store per peer would put a system fence in front of every flag: ~8 serial NVLink round trips.)
+// `flag_a/flag_b` (may be null): two more flags to raise with the same epoch behind the same fence (ghost rows).
 template <int NS>
-__device__ __forceinline__ void publish_sums(const DistLink& dl, int kind, int parity, unsigned int epoch, const double (&v)[NS]) {
-    const int idx = sum_slot_index(kind, parity, dl.rank);
-    for (int p = 0; p < dl.nranks; p++) {
-        SumSlot* s = dl.peer[p] + idx;
+__device__ __forceinline__ void publish_sums(const DistLink& dl, int kind, int parity, unsigned int epoch, const double (&v)[NS],
+                                             unsigned int* flag_a = nullptr, unsigned int* flag_b = nullptr) {
+    const int lane = threadIdx.x & 31;
+    double w[2] = {0.0, 0.0};
 #pragma unroll
-        for (int j = 0; j < NS && j < 2; j++) st_relaxed_sys(&s->v[j], v[j]);
-        st_release_sys(&s->epoch, epoch);
+    for (int j = 0; j < NS && j < 2; j++) w[j] = __shfl_sync(0xffffffffu, v[j], 0);
+    SumSlot* s = nullptr;
+    if (lane < dl.nranks) {
+        s = dl.peer[lane] + sum_slot_index(kind, parity, dl.rank);
+#pragma unroll
+        for (int j = 0; j < NS && j < 2; j++) st_relaxed_sys(&s->v[j], w[j]);
     }
+    __threadfence_system();
+    if (s != nullptr) st_relaxed_sys_u32(&s->epoch, epoch);
+    if (lane == 30 && flag_a != nullptr) st_relaxed_sys_u32(flag_a, epoch);
+    if (lane == 31 && flag_b != nullptr) st_relaxed_sys_u32(flag_b, epoch);
 }
 
 // Whole block: the global sums = slots of rank 0, 1, ... added in that order (the same bits on every rank).

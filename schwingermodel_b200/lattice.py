@@ -135,9 +135,13 @@ class Lattice:
         check(self.lib.sm_set_cg(self.ctx, float(tol), int(max_iter)))
         self.tol, self.max_iter = float(tol), int(max_iter)
 
-    def set_solver(self, mixed_precision: bool):
-        """False: the reference's double-precision CG (default).  True: opt-in mixed-precision defect correction."""
-        check(self.lib.sm_set_solver(self.ctx, _abi.SM_SOLVER_MIXED if mixed_precision else _abi.SM_SOLVER_REFERENCE))
+    def set_solver(self, mixed_precision=False):
+        """False / "reference": the reference's double-precision CG (default).  True / "mixed": opt-in mixed-precision
+        defect correction.  "chrono": opt-in chronological start vectors inside a trajectory."""
+        code = {False: _abi.SM_SOLVER_REFERENCE, True: _abi.SM_SOLVER_MIXED, "reference": _abi.SM_SOLVER_REFERENCE,
+                "mixed": _abi.SM_SOLVER_MIXED, "chrono": _abi.SM_SOLVER_CHRONO,
+                "evenodd": _abi.SM_SOLVER_EVENODD}[mixed_precision]
+        check(self.lib.sm_set_solver(self.ctx, code))
 
     def last_kernel_ms(self) -> float:
         ms = C.c_double()
@@ -207,6 +211,15 @@ class Lattice:
         ok, its = C.c_int(0), C.c_int(0)
         check(self.lib.sm_conjugate_gradient(self.ctx, _p(U[0]), _p(U[1]), _p(phi[0]), _p(phi[1]), _p(x[0]), _p(x[1]),
                                              float(m0), C.byref(ok), C.byref(its)))
+        return x, ok.value, its.value
+
+    def evenodd_solve(self, U, phi, m0):
+        """x_e = (Dhat Dhat^dagger)^-1 phi_e on the even sites (opt-in even-odd solver) -> (x, converged, iterations)"""
+        U, phi = _c2(U, self.V), _c2(phi, self.V)
+        x = np.empty_like(phi)
+        ok, its = C.c_int(0), C.c_int(0)
+        check(self.lib.sm_evenodd_solve(self.ctx, _p(U[0]), _p(U[1]), _p(phi[0]), _p(phi[1]), _p(x[0]), _p(x[1]), float(m0),
+                                        C.byref(ok), C.byref(its)))
         return x, ok.value, its.value
 
     def phi_dag_partialD_phi(self, U, left, right):

@@ -698,3 +698,136 @@ def test_mixed_precision_solver_opt_in(sb):
         assert out[1].cg_all_converged == 1
         assert abs(out[0].dH - out[1].dH) <= 1e-5 * max(1.0, abs(out[0].H_old) * 1e-3)
         lat.close()
+
+
+@pytest.mark.parametrize("n", [64, 160, 512], ids=["cluster", "grid-resident", "columns"])
+def test_chronological_start_vector_opt_in(sb, n):
+    """SURVEY 8f.4, opt-in: inside a trajectory the force solves start from the previous solution (second solve) or
+    from the extrapolation of the last two instead of from phi.  Same CG, same stopping rule: every solve converges,
+    fewer D D^dagger applications (a modest saving: CG's count depends on the logarithm of the start residual), the proposal and dH equal the reference solver's far below Metropolis relevance
+    (not to 1e-8: a different iterate), and a solve started from a vector of the caller's meets the stopping rule on
+    the TRUE residual.  BASELINE configs[4] parameters (m0 = -0.18, MD = 20), on every resident CG kernel."""
+    from oracle.port import Port, gaussian_fields
+    beta, m0, md, tau = 2.0, -0.18, 20, 1.0
+    U = Port(n, n).hot_start(12345)
+    chi, pi = gaussian_fields(n, n, 777)
+    lat = sb.Lattice(n, n)
+    out = []
+    for solver in ("reference", "chrono"):
+        lat.set_solver(solver)
+        lat.hmc_configure(beta, m0, md, tau)
+        lat.hmc_set_gauge(U)
+        lat.hmc_inject(pi, chi)
+        r = lat.hmc_trajectory()
+        out.append((r.dH, r.H_old, r.dd_applications, r.cg_all_converged, lat.hmc_get_gauge(True), lat.hmc_get_momenta(True)))
+    lat.set_solver("reference")
+    (dH0, H0, apps0, ok0, U0, p0), (dH1, H1, apps1, ok1, U1, p1) = out
+    assert ok0 == 1 and ok1 == 1
+    assert apps1 < 0.97 * apps0, (apps0, apps1)
+    assert abs(H0 - H1) <= 1e-8                       # the old configuration's solve starts from phi in both
+    assert abs(dH0 - dH1) <= 1e-5 * max(1.0, abs(H0) * 1e-3), (dH0, dH1)
+    assert np.abs(U0 - U1).max() <= 1e-7 and np.abs(p0 - p1).max() <= 1e-6
+    lat.close()
+
+
+def _parity_masks(nx, nt):
+    x, t = np.divmod(np.arange(nx * nt), nt)
+    even = ((x + t) & 1) == 0
+    return even, ~even
+
+
+@pytest.mark.parametrize("nx,nt,m0", [(64, 48, 0.0), (96, 96, -0.18), (256, 256, -0.1)])
+def test_evenodd_solver_opt_in(sb, nx, nt, m0):
+    """SURVEY 8f.4, opt-in: CG on the Schur complement of D on the even sites.  The operator is rebuilt here from the
+    plain stencil (D_phi / D_dagger_phi of the C ABI and parity masks), independently of the even-odd kernels:
+    Dhat v = m v - (1/m) [D ([odd] D v)]_even.  The solution meets the reference's stopping rule on the TRUE residual of
+    Dhat Dhat^dagger x = phi_e, vanishes on the odd sites, equals the even part of the full-lattice solve that the
+    Schur complement stands for, and takes well under the iterations of the reference CG on D D^dagger."""
+    from oracle.port import Port, gaussian_fields
+    P, lat = Port(nx, nt), sb.Lattice(nx, nt)
+    U = P.hot_start(31)
+    phi, _ = gaussian_fields(nx, nt, 32)
+    even, odd = _parity_masks(nx, nt)
+    m = m0 + 2
+    phi_e = phi * even
+
+    def Dhat(v, dagger=False):
+        op = lat.D_dagger_phi if dagger else lat.D_phi
+        w = op(U, v, m0) * odd
+        return (m * v - op(U, w, m0) / m) * even
+
+    x, ok, its = lat.evenodd_solve(U, phi, m0)
+    assert ok == 1 and np.abs(x[:, odd]).max() == 0.0
+    res = phi_e - Dhat(Dhat(x, True))
+    assert np.linalg.norm(res) <= 2e-10 * np.linalg.norm(phi_e)
+    # Schur identity: with z = Dhat^dagger x the full-lattice solution of D y = (phi_e, 0) has y_even = z
+    z = Dhat(x, True)
+    y = z - (lat.D_phi(U, z, m0) * odd) / m               # y_odd = -(1/m) (D z)_odd
+    assert np.linalg.norm(lat.D_phi(U, y, m0) - phi_e) <= 1e-9 * np.linalg.norm(phi_e)
+    _, ok_ref, its_ref = lat.conjugate_gradient(U, phi_e, m0)
+    assert ok_ref == 1 and its < 0.7 * its_ref, (its, its_ref)
+    lat.close()
+
+
+def test_evenodd_hmc_force_reversibility_and_chain(sb):
+    """The opt-in even-odd HMC: pseudofermion on the even sites, S_pf = phi_e^dagger (Dhat Dhat^dagger)^-1 phi_e.
+    Force = -dS/d(omega) by central differences through the Hamiltonian entry point, leapfrog reversibility, and a short
+    chain on 32x32 (beta = 2, m0 = 0): the plaquette agrees with the reference-exact chain's, <exp(-dH)> ~ 1, and a
+    near-critical trajectory spends less than half of the operator applications of the reference solver."""
+    from oracle.port import Port, gaussian_fields
+    g = load_golden(8, 8)
+    lat = sb.Lattice(8, 8)
+    lat.set_solver("evenodd")
+    U, pi, phi = g["U"].copy(), g["pi"], g["phi"]
+    m0, beta = float(g["m0"]), float(g["beta"])
+    lat.set_cg(1e-13, 10000)
+    lat.hmc_configure(beta, m0, 6, 0.5)
+    lat.hmc_set_gauge(U)
+    F, ok = lat.hmc_force(phi)
+    assert ok == 1
+    zero = np.zeros_like(pi)
+    w = 1e-5
+    for mu, n in [(0, 3), (1, 5), (0, 63), (1, 18)]:
+        Up, Um = U.copy(), U.copy()
+        Up[mu, n] *= np.exp(1j * w)
+        Um[mu, n] *= np.exp(-1j * w)
+        lat.hmc_set_gauge(Up)
+        sp = lat.hmc_hamiltonian(zero, phi)
+        lat.hmc_set_gauge(Um)
+        sm = lat.hmc_hamiltonian(zero, phi)
+        dS = (sp - sm) / (2 * w)
+        assert abs(F[mu, n] + dS) < 2e-5 * max(1.0, abs(dS)), (mu, n, F[mu, n], dS)
+    lat.hmc_set_gauge(U)
+    U1, p1, _ = lat.hmc_leapfrog(pi, phi)
+    lat.hmc_set_gauge(U1)
+    U2, p2, _ = lat.hmc_leapfrog(-p1, phi)
+    assert np.abs(U2 - U).max() < 1e-11 and np.abs(p2 + pi).max() < 1e-10
+    lat.close()
+    # chain statistics (SURVEY section 4: 64^2 gives <P> = 0.7187(11); 32^2 agrees within the tolerance used here)
+    n = 32
+    lat = sb.Lattice(n, n)
+    lat.set_solver("evenodd")
+    h = sb.HMC(lat, Port(n, n).hot_start(12345), 10, 1.0, 80, 40, 0, 2.0, 0.0, seed=7)
+    Ep, dEp = h.HMC_algorithm()
+    assert abs(Ep - 0.7187) < 0.02, Ep
+    assert 0.3 < h.getacceptance_rate() <= 1.0
+    dH = np.array([x[0] for x in h.history[80:]])
+    assert abs(np.exp(-dH).mean() - 1.0) < 0.5
+    assert all(ok for (_, _, _, ok, _) in h.history)
+    lat.close()
+    # near the critical mass (BASELINE configs[4] parameters) the even-odd trajectory needs far fewer applications
+    n = 128
+    lat = sb.Lattice(n, n)
+    U = Port(n, n).hot_start(12345)
+    chi, pi = gaussian_fields(n, n, 777)
+    apps = {}
+    for solver in ("reference", "evenodd"):
+        lat.set_solver(solver)
+        lat.hmc_configure(2.0, -0.18, 20, 1.0)
+        lat.hmc_set_gauge(U)
+        lat.hmc_inject(pi, chi)
+        r = lat.hmc_trajectory()
+        assert r.cg_all_converged == 1
+        apps[solver] = r.dd_applications
+    assert apps["evenodd"] < 0.5 * apps["reference"], apps
+    lat.close()

@@ -115,6 +115,64 @@ def test_executable_protocol_and_outputs(tmp_path):
     assert np.abs(np.hypot(rec["re"], rec["im"]) - 1).max() < 1e-12     # links stay on the unit circle
 
 
+_NUM = r"[-+]?(?:\d+\.?\d*|\.\d+)(?:[eE][-+]?\d+)?"
+
+
+def _masked(line):
+    """numbers -> '#', runs of blanks -> one blank"""
+    import re
+    return re.sub(r"\s+", " ", re.sub(_NUM, "#", line)).strip()
+
+
+@pytest.mark.gpu
+def test_executable_transcript_equals_reference_executable(tmp_path):
+    """Same stdin into host/bin/SM_16x24 and into the UNMODIFIED reference's own executable (oracle/_ref/SM_16x24, built
+    from /root/reference/src/main.cpp by oracle/ref_build/build_ref.sh --exe; its transcript of the same input is also
+    committed under tests/golden/ref_exe_16x24/): stderr (banner + prompts) byte for byte; stdout and _SimData.txt line
+    by line -- exactly, except where the line holds a clock, a timing or a Monte-Carlo average (the reference seeds its
+    generators from time(0) and random_device, src/main.cpp:17, src/hmc.cpp:7), where the text with numbers masked and
+    the line's width must agree."""
+    _build(16, 24)
+    params = "1\n1\n-0.05\n12\n0.6\n2\n40\n20\n0\n0\n"
+    env = dict(os.environ, SM_SEED="5", HOSTNAME="testhost")
+    sim_name = "2D_U1_16x24_m0-0.050000000000000003_SimData.txt"
+    mine = tmp_path / "mine"
+    mine.mkdir()
+    r = subprocess.run([os.path.join(BIN, "SM_16x24")], input=params, capture_output=True, text=True, cwd=mine, env=env,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr
+    ref_exe = os.path.join(ROOT, "oracle", "_ref", "SM_16x24")
+    gold = os.path.join(GOLDEN, "ref_exe_16x24")
+    refs = [(open(os.path.join(gold, "stdout.txt")).read(), open(os.path.join(gold, "stderr.txt")).read(),
+             open(os.path.join(gold, "SimData.txt")).read(), "committed transcript")]
+    if os.path.exists(ref_exe):                       # the live reference executable on this box's CPU
+        theirs = tmp_path / "ref"
+        theirs.mkdir()
+        q = subprocess.run([ref_exe], input=params, capture_output=True, text=True, cwd=theirs, env=env, timeout=900)
+        assert q.returncode == 0, q.stderr
+        refs.append((q.stdout, q.stderr, (theirs / sim_name).read_text(), "live reference executable"))
+    my_sim = (mine / sim_name).read_text()
+    volatile_out = ("* Start time:", "Average plaquette value", "Average gauge action", "Acceptance rate:", "Execution time =")
+    for ref_out, ref_err, ref_sim, what in refs:
+        assert r.stderr == ref_err, what
+        a, b = r.stdout.splitlines(), ref_out.splitlines()
+        assert len(a) == len(b), (what, a, b)
+        for x, y in zip(a, b):
+            if x.startswith(volatile_out):
+                assert _masked(x) == _masked(y), (what, x, y)
+            else:
+                assert x == y, (what, x, y)
+        a, b = my_sim.splitlines(), ref_sim.splitlines()
+        assert len(a) == len(b), what
+        for i, (x, y) in enumerate(zip(a, b)):
+            header = b[i - 1] if i else ""
+            if header in ("#Date and time", "#Ep                           #dEp", "#gS                           #dgS",
+                          "#Acceptance rate", "#Execution time"):
+                assert _masked(x) == _masked(y) and (len(x) == len(y) or header == "#Date and time"), (what, x, y)
+            else:
+                assert x == y, (what, i, x, y)
+
+
 @pytest.mark.gpu
 def test_executable_forks_one_rank_per_gpu(tmp_path):
     """ranks_x = 2: the binary forks a second rank itself (no mpirun), NCCL between the two GPUs."""
