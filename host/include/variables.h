@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "config.h"
+#include "schwinger_b200.h"
 
 typedef std::complex<double> c_double;
 extern double pi;
@@ -54,8 +55,7 @@ struct field2 {
     field2& operator=(const field2& o) {
         if (this == &o) return *this;
         if (size != o.size) {
-            delete[] mu0;
-            delete[] mu1;
+            release();
             size = o.size;
             mu0 = new T[size];
             mu1 = new T[size];
@@ -63,16 +63,20 @@ struct field2 {
         copy_from(o);
         return *this;
     }
-    ~field2() {
-        delete[] mu0;
-        delete[] mu1;
-    }
+    ~field2() { release(); }
     void clearBuffer() {
         std::fill(mu0, mu0 + size, T());
         std::fill(mu1, mu1 + size, T());
     }
 
 private:
+    // the library may have page-locked these arrays (sm_host_register): tell it before they go
+    void release() {
+        sm_host_forget(mu0);
+        sm_host_forget(mu1);
+        delete[] mu0;
+        delete[] mu1;
+    }
     void copy_from(const field2& o) {
         std::copy(o.mu0, o.mu0 + size, mu0);
         std::copy(o.mu1, o.mu1 + size, mu1);

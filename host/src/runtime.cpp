@@ -148,6 +148,9 @@ void create_context() {
               "sm_create_dist");
     }
     check(sm_set_cg(g_ctx, CG::tol, CG::max_iter), "sm_set_cg");
+    // the shell's fields are long-lived `new[]` arrays whose destructor tells the library (variables.h): let it
+    // page-lock them so that D_phi(...), conjugate_gradient(...) on host fields copy at the full link rate
+    if (!std::getenv("SM_HOST_REGISTER") || std::atoi(std::getenv("SM_HOST_REGISTER")) != 0) sm_host_register(1);
 }
 
 sm_ctx* ctx() {

@@ -68,6 +68,13 @@ SM_API int sm_nccl_unique_id(void* out_id /* SM_NCCL_ID_BYTES */);
  * ranks' handles in rank order (MPI_Allgather in the reference's world) and every rank connects. */
 SM_API int sm_p2p_handle(sm_ctx* ctx, void* handle_out /* SM_P2P_HANDLE_BYTES */);
 SM_API int sm_p2p_connect(sm_ctx* ctx, const void* all_handles /* nranks * SM_P2P_HANDLE_BYTES, rank order */);
+/* Host-buffer calls copy the caller's arrays (the reference's `new[]`-allocated spinor::mu0/mu1, include/variables.h:54-100)
+   to and from the device.  sm_host_register(1): page-lock every caller buffer the first time it is passed and keep it
+   locked (pointer-keyed cache), so later copies run at the full host-link rate instead of through the driver's pageable
+   staging; the owner must call sm_host_forget(ptr) before freeing such a buffer.  sm_host_register(0) (default) unlocks
+   everything and stops. */
+SM_API int sm_host_register(int enable);
+SM_API int sm_host_forget(const void* ptr);
 /* number of CUDA devices visible to this process; initialises the CUDA runtime, so a launcher that forks one process
    per GPU (the stand-in for `mpirun -n ranks_x*ranks_t`, README.md:49 of the reference) asks from a throw-away child */
 SM_API int sm_device_count(int* n);

@@ -65,6 +65,8 @@ _SIGS = {
     "sm_one_pass_dd": [ctx_p, ip],
     "sm_peer_mode": [ctx_p, ip],
     "sm_device_count": [ip],
+    "sm_host_register": [C.c_int],
+    "sm_host_forget": [C.c_void_p],
     "sm_tables": [ctx_p, C.c_int, C.c_int, C.c_int, ip, ip, dp, dp, ip, ip],
     "sm_D_phi": [ctx_p, dp, dp, dp, dp, dp, dp, C.c_double],
     "sm_D_dagger_phi": [ctx_p, dp, dp, dp, dp, dp, dp, C.c_double],

@@ -314,6 +314,20 @@ int sm_one_pass_dd(const sm_ctx* c, int* one_pass) {
     return SM_OK;
 }
 
+int sm_host_register(int enable) {
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        g_pin_enabled = enable != 0;
+    }
+    if (!enable) host_forget(nullptr);
+    return SM_OK;
+}
+
+int sm_host_forget(const void* ptr) {
+    if (ptr != nullptr) host_forget(ptr);
+    return SM_OK;
+}
+
 int sm_device_count(int* n) {
     NEED(n);
     *n = 0;

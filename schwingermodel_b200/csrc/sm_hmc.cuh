@@ -167,23 +167,76 @@ static int dev_leap_update(sm_ctx* c, cplx* U, double* pi, const double* F, doub
 // ------------------------------------------------------------------------------------------------
 // host <-> device field copies (component arrays of the reference's spinor / re_field)
 // ------------------------------------------------------------------------------------------------
+// Caller buffers of the host-buffer entry points are pageable (`new[]` in the reference's spinor, include/variables.h:
+// 54-100): a copy from pageable memory is staged by the driver and runs at a fraction of the link rate.  Opt-in
+// (sm_host_register(1); the C++ shell in host/ switches it on): page-lock a caller buffer the first time it is seen
+// and remember it by address; the owner calls sm_host_forget(ptr) before it frees the buffer (the shell's field
+// destructor does).  Off by default because a stale entry for memory that was freed and mapped again is a hazard only
+// the owner can rule out.
+struct HostPin {
+    const void* p;
+    size_t bytes;   // 0: registration refused (e.g. already page-locked by its owner): do not try again
+};
+static std::mutex g_pin_mu;
+static std::vector<HostPin> g_pins;
+static bool g_pin_enabled = false;
+
+static void host_pin(const void* p, size_t bytes) {
+    if (!g_pin_enabled || bytes < ((size_t)1 << 16)) return;
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    for (auto& e : g_pins)
+        if (e.p == p) {
+            if (e.bytes == 0 || e.bytes >= bytes) return;
+            cudaHostUnregister((void*)p);          // grew: pin again below
+            e = g_pins.back();
+            g_pins.pop_back();
+            break;
+        }
+    if (g_pins.size() >= 256) return;
+    const cudaError_t err = cudaHostRegister((void*)p, bytes, cudaHostRegisterDefault);
+    if (err != cudaSuccess) cudaGetLastError();
+    g_pins.push_back({p, err == cudaSuccess ? bytes : 0});
+}
+
+static void host_forget(const void* p) {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    for (size_t i = 0; i < g_pins.size(); i++)
+        if (g_pins[i].p == p || p == nullptr) {
+            if (g_pins[i].bytes) {
+                if (cudaHostUnregister((void*)g_pins[i].p) != cudaSuccess) cudaGetLastError();
+            }
+            g_pins[i] = g_pins.back();
+            g_pins.pop_back();
+            if (p != nullptr) return;
+            i--;
+        }
+}
+
 static int h2d_c(sm_ctx* c, cplx* d, const double* h0, const double* h1) {
     invalidate_gauge_ghosts(c, d);
+    host_pin(h0, sizeof(cplx) * c->V);
+    host_pin(h1, sizeof(cplx) * c->V);
     CU(cudaMemcpyAsync(d, h0, sizeof(cplx) * c->V, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(d + c->V, h1, sizeof(cplx) * c->V, cudaMemcpyHostToDevice, c->stream));
     return SM_OK;
 }
 static int d2h_c(sm_ctx* c, const cplx* d, double* h0, double* h1) {
+    host_pin(h0, sizeof(cplx) * c->V);
+    host_pin(h1, sizeof(cplx) * c->V);
     CU(cudaMemcpyAsync(h0, d, sizeof(cplx) * c->V, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(h1, d + c->V, sizeof(cplx) * c->V, cudaMemcpyDeviceToHost, c->stream));
     return SM_OK;
 }
 static int h2d_r(sm_ctx* c, double* d, const double* h0, const double* h1) {
+    host_pin(h0, sizeof(double) * c->V);
+    host_pin(h1, sizeof(double) * c->V);
     CU(cudaMemcpyAsync(d, h0, sizeof(double) * c->V, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(d + c->V, h1, sizeof(double) * c->V, cudaMemcpyHostToDevice, c->stream));
     return SM_OK;
 }
 static int d2h_r(sm_ctx* c, const double* d, double* h0, double* h1) {
+    host_pin(h0, sizeof(double) * c->V);
+    host_pin(h1, sizeof(double) * c->V);
     CU(cudaMemcpyAsync(h0, d, sizeof(double) * c->V, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(h1, d + c->V, sizeof(double) * c->V, cudaMemcpyDeviceToHost, c->stream));
     return SM_OK;
