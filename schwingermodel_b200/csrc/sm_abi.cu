@@ -257,6 +257,7 @@ int sm_destroy(sm_ctx* c) {
     if (c->coop_wsum) cudaFree(c->coop_wsum);
     if (c->coop_bar) cudaFree(c->coop_bar);
     for (auto& g : c->cg_graphs) cudaGraphExecDestroy(g.exec);
+    for (auto& g : c->eo_graphs) cudaGraphExecDestroy(g.exec);
     if (c->h) cudaFreeHost(c->h);
     cudaEventDestroy(c->ev_a);
     cudaEventDestroy(c->ev_b);

@@ -471,27 +471,71 @@ static int dev_cg_eo(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double 
                                                            c->tickets + TK_DOT, &st->phi_norm2);
     KCHECK();
     c->launches++;
-    const int batch = 8;
-    int k = 0, slot = 0, prev = -1;
-    for (;;) {
-        const int k_end = std::min(max_iter, k + batch);
-        for (; k < k_end; k++) {
-            const int cur = k & 1;
-            if (k > 0) {
-                k_cg_dir<<<c->flat_blocks_c, kBlock, 0, c->stream>>>(st, k, tol, c->cg_r, c->cg_d, n_elems);
-                KCHECK();
-                c->launches++;
-            }
-            TRY((dev_Dhat<true>(c, U, c->cg_d, c->tmp, c->eo_t, m0, nullptr, nullptr, done)));
-            TRY((dev_Dhat<false>(c, U, c->eo_t, c->tmp, c->cg_Ad, m0, c->cg_d, st->dAd, done)));
-            k_cg_update<<<c->flat_blocks_c, kBlock, 0, c->stream>>>(st, cur, x, c->cg_d, c->cg_r, c->cg_Ad, n_elems,
-                                                                    c->partials, c->tickets + TK_UPDATE, &st->rr[cur ^ 1]);
+    // one iteration (6 kernels); the iteration index lives in the device state, so a batch of 8 starting on an odd k
+    // is one CUDA graph whatever k is (as in cg_fused_loop)
+    auto iteration = [&](int k) -> int {
+        const int cur = k & 1;
+        if (k > 0) {
+            k_cg_dir_dev<<<c->flat_blocks_c, kBlock, 0, c->stream>>>(st, cur, c->cg_r, c->cg_d, n_elems);
             KCHECK();
             c->launches++;
         }
-        k_cg_check<<<1, 1, 0, c->stream>>>(st, k, tol, max_iter);
+        TRY((dev_Dhat<true>(c, U, c->cg_d, c->tmp, c->eo_t, m0, nullptr, nullptr, done)));
+        TRY((dev_Dhat<false>(c, U, c->eo_t, c->tmp, c->cg_Ad, m0, c->cg_d, st->dAd, done)));
+        k_cg_update<<<c->flat_blocks_c, kBlock, 0, c->stream>>>(st, cur, x, c->cg_d, c->cg_r, c->cg_Ad, n_elems, c->partials,
+                                                                c->tickets + TK_UPDATE, &st->rr[cur ^ 1]);
         KCHECK();
         c->launches++;
+        return SM_OK;
+    };
+    const int batch = 8;
+    cudaGraphExec_t exec = nullptr;
+    int graph_kernels = 0;
+    const bool graphs = c->use_graphs && max_iter > batch;
+    if (graphs) {
+        for (auto& g : c->eo_graphs)
+            if (g.U == (const void*)U && g.x == (const void*)x && g.m0 == m0) {
+                exec = g.exec;
+                graph_kernels = g.kernels;
+            }
+    }
+    int k = 0, slot = 0, prev = -1;
+    TRY(iteration(k++));
+    if (graphs && exec == nullptr) {
+        const long long l0 = c->launches;
+        cudaGraph_t graph = nullptr;
+        CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = SM_OK;
+        for (int i = 0; i < batch && rc == SM_OK; i++) rc = iteration(1 + i);
+        if (rc == SM_OK) {
+            k_cg_check_dev<<<1, 1, 0, c->stream>>>(st, DistLink{});
+            c->launches++;
+        }
+        cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+        if (rc != SM_OK) return rc;
+        if (e != cudaSuccess) return fail(SM_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+        graph_kernels = (int)(c->launches - l0);
+        c->launches = l0;
+        CU(cudaGraphInstantiate(&exec, graph, 0));
+        cudaGraphDestroy(graph);
+        if (c->eo_graphs.size() >= 16) {
+            cudaGraphExecDestroy(c->eo_graphs.front().exec);
+            c->eo_graphs.erase(c->eo_graphs.begin());
+        }
+        c->eo_graphs.push_back({(const void*)U, (const void*)x, m0, exec, graph_kernels});
+    }
+    for (;;) {
+        if (exec != nullptr && k + batch <= max_iter) {
+            CU(cudaGraphLaunch(exec, c->stream));
+            c->launches += graph_kernels;
+            k += batch;
+        } else {
+            const int k_end = std::min(max_iter, k + batch);
+            for (; k < k_end; k++) TRY(iteration(k));
+            k_cg_check_dev<<<1, 1, 0, c->stream>>>(st, DistLink{});
+            KCHECK();
+            c->launches++;
+        }
         CU(cudaMemcpyAsync(&c->h->cg[slot], st, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
         CU(cudaEventRecord(c->ev_poll[slot], c->stream));
         if (prev >= 0) {

@@ -186,6 +186,7 @@ struct sm_ctx {
         int kernels;
     };
     std::vector<CgGraph> cg_graphs;
+    std::vector<CgGraph> eo_graphs;   // ... and of the even-odd solver
     bool use_graphs = true;
     unsigned int attr_done = 0;   // kernel attributes already set on this context's device
     int solver = SM_SOLVER_REFERENCE;

@@ -400,7 +400,10 @@ __global__ void __launch_bounds__(kBlock) k_cg_update(CgState* st, int cur, cplx
         acc[0] += rv.x * rv.x + rv.y * rv.y;
     }
     if (grid_reduce<1>(acc, partials, ticket)) {
-        if (threadIdx.x == 0) sums_out[0] = acc[0];
+        if (threadIdx.x == 0) {
+            sums_out[0] = acc[0];
+            st->k = st->k + 1;      // iterations done (read by the graph-replayed even-odd loop; unused by the two-pass path)
+        }
     }
 }
 
@@ -416,6 +419,29 @@ __global__ void __launch_bounds__(kBlock) k_cg_dir(CgState* st, int k, double to
     if (cg_converged(st, cur, tol)) {
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             st->iters = k - 1;
+            st->converged = 1;
+            st->done = 1;
+        }
+        return;
+    }
+    const double beta = st->rr[cur] / st->rr[cur ^ 1];
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += stride) {
+        const cplx rv = ld_stream(r + i);
+        cplx dv = d[i];
+        dv.x = dv.x * beta + rv.x;
+        dv.y = dv.y * beta + rv.y;
+        d[i] = dv;
+    }
+}
+
+// the same with the iteration index read from the device state (kernel arguments independent of the iteration: CUDA graphs)
+__global__ void __launch_bounds__(kBlock) k_cg_dir_dev(CgState* st, int cur, const cplx* __restrict__ r,
+                                                       cplx* __restrict__ d, int n_elems) {
+    if (st->done) return;
+    if (cg_converged(st, cur, st->tol)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            st->iters = st->k - 1;
             st->converged = 1;
             st->done = 1;
         }
