@@ -237,6 +237,7 @@ int sm_destroy(sm_ctx* c) {
     if (c->push_ticket) cudaFree(c->push_ticket);
     if (c->comm) g_nccl.CommDestroy(c->comm);
     if (c->eo_t) cudaFree(c->eo_t);
+    if (c->eo_wsum) cudaFree(c->eo_wsum);
     if (c->chrono_prev) cudaFree(c->chrono_prev);
     if (c->chrono_guess) cudaFree(c->chrono_guess);
     void* ptrs[] = {c->partials, c->tickets, c->cg,      c->sums,    c->sums_loc, c->tmp,     c->cg_r,   c->cg_d,

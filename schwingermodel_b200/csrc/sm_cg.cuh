@@ -451,7 +451,58 @@ static int dev_cg_cols(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, doubl
 // (src/conjugate_gradient.cpp:4-67), another operator: its condition number is ~4x smaller near the critical mass
 // (lambda_hat = lambda_+ lambda_- / m), so the solve takes a fraction of the iterations.  phi, x: full-lattice arrays,
 // zero on the odd sites.  Iterations are launched in batches; the host polls the device scalars one batch behind.
+// the whole even-odd solve in one cooperative launch (sm_evenodd_cg.cuh) while the working set of 7 fields lives in L2
+static bool eo_coop_ok(sm_ctx* c) {
+    if (c->eo_coop < 0) {
+        c->eo_coop = 0;
+        int coop = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
+        const char* e = getenv("SM_EO_COOP");
+        if (coop && !(e && atoi(e) == 0) && c->use_cluster && (long long)c->V <= (1LL << 21) &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_eo_coop, kEoThreads, 0) == cudaSuccess && per_sm >= 1)
+            c->eo_coop = 1;
+        cudaGetLastError();
+    }
+    return c->eo_coop == 1;
+}
+
+static int dev_cg_eo_coop(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, int* converged, int* iterations) {
+    TRY(ensure_complex(c, &c->tmp));
+    TRY(ensure_complex(c, &c->eo_t));
+    TRY(ensure_complex(c, &c->cg_r));
+    TRY(ensure_complex(c, &c->cg_d));
+    TRY(ensure_complex(c, &c->cg_Ad));
+    if (!c->eo_wsum) TRY(dev_alloc(&c->eo_wsum, (size_t)4 * kGridSyncMaxCtas));
+    if (!c->coop_bar) TRY(dev_alloc(&c->coop_bar, (size_t)32));
+    CU(cudaMemsetAsync(c->coop_bar, 0, sizeof(unsigned int) * 32, c->stream));
+    EoCgArgs a{};
+    a.U = U;
+    a.phi = phi;
+    a.x = x;
+    a.r = c->cg_r;
+    a.d = c->cg_d;
+    a.t = c->eo_t;
+    a.W = c->tmp;
+    a.Ad = c->cg_Ad;
+    a.wx = c->wx;
+    a.wt = c->wt;
+    a.V = c->V;
+    a.mass = m0 + 2;
+    a.sR_edge = c->sR_edge();
+    a.sL_edge = c->sL_edge();
+    a.tol = c->tol;
+    a.max_iter = c->max_iter;
+    a.st = c->cg;
+    a.wsum = c->eo_wsum;
+    a.bar = c->coop_bar;
+    const int blocks = std::min(c->sm_count, kGridSyncMaxCtas);
+    void* params[] = {&a};
+    CU(cudaLaunchCooperativeKernel((const void*)k_cg_eo_coop, dim3(blocks, 1, 1), dim3(kEoThreads, 1, 1), params, 0, c->stream));
+    return resident_finish(c, converged, iterations);
+}
+
 static int dev_cg_eo(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, int* converged, int* iterations) {
+    if (eo_coop_ok(c)) return dev_cg_eo_coop(c, U, phi, x, m0, converged, iterations);
     TRY(ensure_complex(c, &c->tmp));
     TRY(ensure_complex(c, &c->eo_t));
     TRY(ensure_complex(c, &c->cg_r));

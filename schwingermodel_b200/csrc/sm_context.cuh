@@ -22,6 +22,7 @@
 #include "sm_fused.cuh"
 #include "sm_fused_tma.cuh"
 #include "sm_cluster_cg.cuh"
+#include "sm_evenodd_cg.cuh"
 
 using namespace sm;
 // ------------------------------------------------------------------------------------------------
@@ -139,6 +140,8 @@ struct sm_ctx {
     // work fields (2V complex each)
     cplx *tmp = nullptr, *cg_r = nullptr, *cg_d = nullptr, *cg_Ad = nullptr, *cg_d2 = nullptr;
     cplx* eo_t = nullptr;   // even-odd solver: Dhat^dagger d
+    double* eo_wsum = nullptr;
+    int eo_coop = -1;       // cooperative even-odd CG usable on this device / lattice (-1: not asked yet; SM_EO_COOP=0 disables)
     // staging for the host-buffer API
     cplx *sU = nullptr, *sA = nullptr, *sB = nullptr, *sC = nullptr;
     double* sF = nullptr;

@@ -117,7 +117,15 @@ struct WilsonArgs {
     int interior_blocks;   // (boundary launch) blocks of the interior launch
 };
 
-template <bool DAG>
+// COH: the input field is being written by other blocks of the same (cooperative) kernel between grid barriers, so it is
+// read with ld.cg (L2) instead of the non-coherent read-only path.  SELF = false: the site's own value is known to be zero
+// (even-odd fields, output parity != input parity) and is not read: out = -1/2 sum(hops).
+template <bool COH>
+__device__ __forceinline__ cplx ld_in(const cplx* p) {
+    return COH ? __ldcg(p) : __ldg(p);
+}
+
+template <bool DAG, bool COH = false, bool SELF = true>
 __device__ __forceinline__ void wilson_site(const WilsonArgs& a, int x, int t, cplx& o0, cplx& o1) {
     constexpr double s = DAG ? 1.0 : -1.0;
     const int wt = a.wt, wx = a.wx, V = a.V;
@@ -127,7 +135,11 @@ __device__ __forceinline__ void wilson_site(const WilsonArgs& a, int x, int t, c
     const cplx* __restrict__ U0 = a.U;
     const cplx* __restrict__ U1 = a.U + V;
 
-    const cplx c0 = ldg(in0 + n), c1 = ldg(in1 + n);
+    cplx c0 = make_double2(0.0, 0.0), c1 = c0;
+    if (SELF) {
+        c0 = ld_in<COH>(in0 + n);
+        c1 = ld_in<COH>(in1 + n);
+    }
     const cplx u0 = ldg(U0 + n), u1 = ldg(U1 + n);
     cplx acc0, acc1;
 
@@ -138,7 +150,7 @@ __device__ __forceinline__ void wilson_site(const WilsonArgs& a, int x, int t, c
             h = ldg(a.g_tp + x);
         } else {
             const int m = nb_tp(n, t, wt);
-            const cplx p0 = ldg(in0 + m), p1 = ldg(in1 + m);
+            const cplx p0 = ld_in<COH>(in0 + m), p1 = ld_in<COH>(in1 + m);
             h = make_double2(p0.x + s * p1.x, p0.y + s * p1.y);
         }
         cplx v = cmul(u0, h);
@@ -153,7 +165,7 @@ __device__ __forceinline__ void wilson_site(const WilsonArgs& a, int x, int t, c
             h = ldg(a.g_xp + t);
         } else {
             const int m = nb_xp(n, x, wx, wt);
-            const cplx p0 = ldg(in0 + m), p1 = ldg(in1 + m);
+            const cplx p0 = ld_in<COH>(in0 + m), p1 = ld_in<COH>(in1 + m);
             h = make_double2(p0.x + s * p1.y, p0.y - s * p1.x);
         }
         const cplx v = cmul(u1, h);
@@ -168,7 +180,7 @@ __device__ __forceinline__ void wilson_site(const WilsonArgs& a, int x, int t, c
             v = ldg(a.g_tm + x);
         } else {
             const int m = nb_tm(n, t, wt);
-            const cplx p0 = ldg(in0 + m), p1 = ldg(in1 + m);
+            const cplx p0 = ld_in<COH>(in0 + m), p1 = ld_in<COH>(in1 + m);
             const cplx h = make_double2(p0.x - s * p1.x, p0.y - s * p1.y);
             v = cmulc(ldg(U0 + m), h);
         }
@@ -184,7 +196,7 @@ __device__ __forceinline__ void wilson_site(const WilsonArgs& a, int x, int t, c
             v = ldg(a.g_xm + t);
         } else {
             const int m = nb_xm(n, x, wx, wt);
-            const cplx p0 = ldg(in0 + m), p1 = ldg(in1 + m);
+            const cplx p0 = ld_in<COH>(in0 + m), p1 = ld_in<COH>(in1 + m);
             const cplx h = make_double2(p0.x - s * p1.y, p0.y + s * p1.x);
             v = cmulc(ldg(U1 + m), h);
         }
