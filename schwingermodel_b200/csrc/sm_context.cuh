@@ -308,7 +308,8 @@ static int ctx_common_init(sm_ctx* c) {
         const long long V = (long long)c->wx * c->wt;
         int BT = (c->wt + 4 <= 128 || V <= (1LL << 21)) ? 128 : 256;
         if (const char* e = getenv("SM_FUSED_BT")) BT = atoi(e) == 128 ? 128 : 256;
-        const int strips = (c->wt + (BT - 4) - 1) / (BT - 4);
+        int strips = (c->wt + (BT - 4) - 1) / (BT - 4);
+        if (const char* e = getenv("SM_FUSED_STRIPS")) strips = std::max(strips, atoi(e));   // more, narrower strips
         c->fus_cols = (c->wt + strips - 1) / strips;     // equal strips
         const int capacity = c->sm_count * (BT == 128 ? 4 : 2);
         // rows per chunk: minimise  waves x (rows + 4 warm-up rows)  with waves = ceil(blocks / resident blocks);

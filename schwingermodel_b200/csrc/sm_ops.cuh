@@ -239,6 +239,8 @@ static int launch_fused(sm_ctx* c, const C* U, const C* in, C* out, double m0, d
     unsigned int attr_bit = 1u << (MODE + (kDouble ? 0 : 4));
     if constexpr (kDouble) {
         if (c->fused_tma) {
+            // (a third stage for the CG pass -- 128-thread blocks, 3 per SM -- was measured and dropped: 65-74 us per
+            // iteration at 1024^2 against 63.7; profiles/r02_cg_1024_l2_persistence.txt)
             if (MODE != FUSED_CG && c->fused_stages == 4) {
                 kern = k_dd_tma<MODE, (MODE == FUSED_CG) ? 2 : 4>;
                 smem = fused_tma_smem_bytes(MODE, (MODE == FUSED_CG) ? 2 : 4, c->fus_block.x);
