@@ -236,6 +236,13 @@ int sm_destroy(sm_ctx* c) {
     if (c->win) cudaFree(c->win);
     if (c->push_ticket) cudaFree(c->push_ticket);
     if (c->comm) g_nccl.CommDestroy(c->comm);
+    for (int kind = 0; kind < 5; kind++)
+        for (int side = 0; side < 2; side++) {
+            if (c->tg_col[kind][side]) cudaFree(c->tg_col[kind][side]);
+            if (c->tg_row[kind][side]) cudaFree(c->tg_row[kind][side]);
+        }
+    if (c->tg_sendc) cudaFree(c->tg_sendc);
+    if (c->tg_sendr) cudaFree(c->tg_sendr);
     if (c->eo_t) cudaFree(c->eo_t);
     if (c->eo_wsum) cudaFree(c->eo_wsum);
     if (c->chrono_prev) cudaFree(c->chrono_prev);
@@ -487,7 +494,7 @@ int sm_phi_dag_partialD_phi(sm_ctx* c, const double* U0, const double* U1, const
     TRY(h2d_c(c, c->sU, U0, U1));
     TRY(h2d_c(c, c->sA, l0, l1));
     TRY(h2d_c(c, c->sB, r0, r1));
-    c->ghost_valid_for = c->f2_U_valid_for = nullptr;
+    c->ghost_valid_for = c->f2_U_valid_for = c->tg_U_valid_for = nullptr;
     tick(c);
     TRY(dev_force(c, c->sU, c->sA, c->sB, c->sF, 0.0, true, false));
     TRY(tock(c));
@@ -500,7 +507,7 @@ int sm_compute_staple(sm_ctx* c, const double* U0, const double* U1, double* K0,
     NEED(U0); NEED(U1); NEED(K0); NEED(K1);
     TRY(ensure_staging(c));
     TRY(h2d_c(c, c->sU, U0, U1));
-    c->ghost_valid_for = c->f2_U_valid_for = nullptr;
+    c->ghost_valid_for = c->f2_U_valid_for = c->tg_U_valid_for = nullptr;
     tick(c);
     TRY(refresh_gauge_ghosts(c, c->sU));
     k_staple<<<c->flat_blocks_s, kBlock, 0, c->stream>>>(gauge_view(c, c->sU), c->sB);
@@ -516,7 +523,7 @@ int sm_compute_plaquette(sm_ctx* c, const double* U0, const double* U1, double b
     NEED(U0); NEED(U1); NEED(sums);
     TRY(ensure_staging(c));
     TRY(h2d_c(c, c->sU, U0, U1));
-    c->ghost_valid_for = c->f2_U_valid_for = nullptr;
+    c->ghost_valid_for = c->f2_U_valid_for = c->tg_U_valid_for = nullptr;
     tick(c);
     TRY(dev_plaquette(c, c->sU, beta, P ? c->sA : nullptr, c->sums));
     TRY(tock(c));
@@ -629,7 +636,7 @@ int sm_hmc_set_gauge(sm_ctx* c, const double* U0, const double* U1) {
     TRY(set_device(c));
     NEED(U0); NEED(U1);
     TRY(hmc_alloc(c));
-    c->ghost_valid_for = c->f2_U_valid_for = nullptr;
+    c->ghost_valid_for = c->f2_U_valid_for = c->tg_U_valid_for = nullptr;
     TRY(h2d_c(c, c->U, U0, U1));
     c->hmc_has_gauge = true;
     return sync(c);
@@ -694,6 +701,7 @@ int sm_hmc_trajectory(sm_ctx* c, sm_traj_result* out) {
     if (!c->hmc_has_gauge) return fail(SM_ERR_STATE, "sm_hmc_set_gauge first");
     if (!c->hmc_has_fields) return fail(SM_ERR_STATE, "sm_hmc_refresh or sm_hmc_inject first");
     if (c->hp.md_steps < 1) return fail(SM_ERR_STATE, "sm_hmc_configure first");
+    NvtxRange nvtx("sm:HMC_Update trajectory");
     TrajAcc acc;
     CU(cudaEventRecord(c->ev_t0, c->stream));
     TRY(hmc_pseudofermion(c));                                            // hmc.cpp:160
@@ -728,7 +736,7 @@ int sm_hmc_accept(sm_ctx* c, int accept) {
     if (!c->hmc_has_gauge) return fail(SM_ERR_STATE, "no gauge field set");
     if (accept) {   // GConf = GConf_copy (hmc.cpp:173) as a pointer swap
         std::swap(c->U, c->Up);
-        c->ghost_valid_for = c->f2_U_valid_for = nullptr;
+        c->ghost_valid_for = c->f2_U_valid_for = c->tg_U_valid_for = nullptr;
     }
     return SM_OK;
 }

@@ -502,6 +502,7 @@ static int dev_cg_eo_coop(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, do
 }
 
 static int dev_cg_eo(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, int* converged, int* iterations) {
+    NvtxRange nvtx("sm:conjugate_gradient(even-odd)");
     if (eo_coop_ok(c)) return dev_cg_eo_coop(c, U, phi, x, m0, converged, iterations);
     TRY(ensure_complex(c, &c->tmp));
     TRY(ensure_complex(c, &c->eo_t));
@@ -620,6 +621,7 @@ static int dev_cg_route(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, doub
 // recurrences, the stopping rule |r| < tol |phi| -- is the same; only the opt-in chronological solver passes one.
 static int dev_cg(sm_ctx* c, const cplx* U, const cplx* phi, cplx* x, double m0, int* converged, int* iterations,
                   const cplx* x0 = nullptr) {
+    NvtxRange nvtx("sm:conjugate_gradient");
     c->cg_x0 = (c->solver == SM_SOLVER_MIXED) ? nullptr : x0;
     const int rc = dev_cg_route(c, U, phi, x, m0, converged, iterations);
     c->cg_x0 = nullptr;

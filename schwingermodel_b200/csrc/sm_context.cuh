@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <cmath>
@@ -52,6 +53,15 @@ static int fail(int code, const std::string& msg) {
     do {                                                                         \
         if ((p) == nullptr) return fail(SM_ERR_ARG, std::string("null argument: ") + #p); \
     } while (0)
+
+// NVTX ranges around the phases of the path (CG solve, force, link/momentum update, Hamiltonian, trajectory): visible in
+// Nsight Systems / Compute timelines; header-only (nvtx3), a few nanoseconds when no tool is attached.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 // ------------------------------------------------------------------------------------------------
 // NCCL, bound lazily so that single-GPU use never loads it (and a process that already holds
@@ -164,6 +174,14 @@ struct sm_ctx {
     cplx *f2_U[2] = {nullptr, nullptr}, *f2_in[2] = {nullptr, nullptr}, *f2_r[2] = {nullptr, nullptr};
     cplx *f2_d[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [ping-pong][lo/hi]
     const cplx* f2_U_valid_for = nullptr;
+    // one-pass D D^dagger on lattices split along t (sm_ops.cuh: launch_fused_tsplit): 2-deep ghost columns [comp][wx][2]
+    // and ghost rows widened to wt + 4 (corner entries); kinds: 0 U, 1 psi, 2 r, 3/4 the d ping-pong
+    bool tsplit_onepass = true;      // SM_TSPLIT_ONEPASS=0: keep the two-pass kernels on t-splits
+    bool self_t = false, self_x = false;   // SM_SELF_GHOSTS=t|x|xt (tests, one GPU): a single tile that takes its own opposite edges as ghosts
+    cplx* tg_col[5][2] = {};         // [kind][lo, hi]
+    cplx* tg_row[5][2] = {};
+    cplx *tg_sendc = nullptr, *tg_sendr = nullptr;
+    const cplx* tg_U_valid_for = nullptr;
     // peer-memory halo push (sm_p2p_connect): one window per rank, [kind: psi, r][parity][side: lo, hi][4 wt]
     // complex + 4 epoch flags; neighbours store into it over NVLink
     cplx* win = nullptr;
@@ -257,6 +275,11 @@ static int ctx_common_init(sm_ctx* c) {
     if (const char* e = getenv("SM_OVERLAP")) c->overlap = atoi(e) != 0;
     if (const char* e = getenv("SM_GRAPHS")) c->use_graphs = atoi(e) != 0;
     if (const char* e = getenv("SM_FUSED_TMA")) c->fused_tma = atoi(e) != 0;
+    if (const char* e = getenv("SM_TSPLIT_ONEPASS")) c->tsplit_onepass = atoi(e) != 0;
+    if (const char* e = getenv("SM_SELF_GHOSTS")) {
+        c->self_t = strchr(e, 't') != nullptr && c->nranks == 1;
+        c->self_x = strchr(e, 'x') != nullptr && c->nranks == 1;
+    }
     if (const char* e = getenv("SM_FUSED_STAGES")) c->fused_stages = atoi(e) == 3 ? 3 : 4;
     if (const char* e = getenv("SM_CLUSTER_CG")) c->use_cluster = atoi(e) != 0;
     if (const char* e = getenv("SM_COLS")) {      // "0": off; "S,T": force a variant

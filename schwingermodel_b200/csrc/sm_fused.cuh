@@ -64,6 +64,19 @@ struct FusedArgsT {
     C* gd_lo;          // CG: ghost rows of d_k, written here for the next iteration
     C* gd_hi;
     DistLink dl;       // CG on a split lattice with peer-memory sums and halos (sm_peer.cuh); dl.on == 0 otherwise
+    // lattice split along t (k_dd_tma only): 2-deep ghost COLUMNS, layout [component][wx rows][2]: columns -2,-1 ("lo", from
+    // the -t neighbour) and wt, wt+1 ("hi").  With them the ghost ROW arrays are row_w = wt + 4 wide and start at column
+    // -2 (they carry the corner entries of a 2-D split); without, row_w = wt.  tg_on == 0: wrap in t inside the tile.
+    int tg_on;
+    int row_w;
+    const C* tgU_lo;
+    const C* tgU_hi;
+    const C* tgin_lo;  // psi (PLAIN/DOT) or d_{k-1} (CG)
+    const C* tgin_hi;
+    const C* tgr_lo;   // CG: r
+    const C* tgr_hi;
+    C* tgd_lo;         // CG: ghost columns of d_k, written by the edge strips for the next iteration
+    C* tgd_hi;
 };
 
 typedef FusedArgsT<cplx> FusedArgs;

@@ -131,23 +131,64 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_tma(const FusedArgsT<cplx> a) 
     //      arrays lane 16 of warp w takes array w + #warps).  Where row j of an array lives -- the tile, wrapped in x
     //      on a single tile, or a 2-row ghost array on a lattice split along x -- is tabulated once in shared memory
     //      as three row pointers per array: row -2 ("lo"), row 0 (tile), row wx ("hi").
-    __shared__ const C* s_src[8][3];
+    //      With ghost columns (lattice split along t) the two halo columns each side of the tile come from packed
+    //      [row][2] arrays (or, in ghost rows of a 2-D split, from the corner entries of the widened ghost-row arrays)
+    //      instead of from the wrapped columns of the same row: three pointers per array and region -- main piece,
+    //      left piece (column -2), right piece (column wt) -- and their row strides.
+    __shared__ const C* s_src[8][3][3];     // [array][region: rows < 0, tile, rows >= wx][piece: main, left, right]
+    __shared__ int s_stride[3][2];          // [region][main, side] row stride in elements
     const int nwarps = BT >> 5;
     const int lane = tid & 31, warp = tid >> 5;
     const int my_arr = (NARR > nwarps) ? warp + nwarps * (lane >> 4) : warp;
     const bool issuer = ((NARR > nwarps) ? (lane & 15) == 0 : lane == 0) && my_arr < NARR;
     const bool split = (a.gU_lo != nullptr);
+    const bool tg = (a.tg_on != 0);
+    const int row_w = tg ? a.row_w : wt;            // width of the ghost-row arrays
+    const int row_off = (row_w - wt) >> 1;          // their column of tile column 0 (2 with corners)
     if (tid < NARR) {
         const int kind = tid >> 1, comp = tid & 1;   // kind 0: U ; 1: in (PLAIN/DOT) or r (CG) ; 2: d_{k-1} ; 3: x
-        const C *tile, *lo, *hi;
-        if (kind == 0) { tile = a.U; lo = a.gU_lo; hi = a.gU_hi; }
-        else if (kind == 1 && MODE == FUSED_CG) { tile = a.r; lo = a.gr_lo; hi = a.gr_hi; }
-        else if (kind == 3) { tile = a.x; lo = hi = nullptr; }          // own rows only: never a ghost row
-        else { tile = a.in; lo = a.gin_lo; hi = a.gin_hi; }
+        const C *tile, *lo, *hi, *cl, *ch;
+        if (kind == 0) { tile = a.U; lo = a.gU_lo; hi = a.gU_hi; cl = a.tgU_lo; ch = a.tgU_hi; }
+        else if (kind == 1 && MODE == FUSED_CG) { tile = a.r; lo = a.gr_lo; hi = a.gr_hi; cl = a.tgr_lo; ch = a.tgr_hi; }
+        else if (kind == 3) { tile = a.x; lo = hi = cl = ch = nullptr; }   // own rows, owner columns only
+        else { tile = a.in; lo = a.gin_lo; hi = a.gin_hi; cl = a.tgin_lo; ch = a.tgin_hi; }
         tile += (size_t)comp * V;
-        s_src[tid][1] = tile;
-        s_src[tid][0] = (split && lo) ? lo + (size_t)comp * 2 * wt : tile + (size_t)(wx - 2) * wt;
-        s_src[tid][2] = (split && hi) ? hi + (size_t)comp * 2 * wt : tile;
+        const bool colg = tg && cl != nullptr;
+        if (colg) {
+            cl += (size_t)comp * 2 * wx;
+            ch += (size_t)comp * 2 * wx;
+        }
+        // tile rows
+        s_src[tid][1][0] = tile;
+        s_src[tid][1][1] = colg ? cl : tile + (wt - 2);
+        s_src[tid][1][2] = colg ? ch : tile;
+        // rows -2, -1 and wx, wx+1: ghost rows of a split along x, else the tile's own rows wx-2.. / 0..
+        if (split && lo) {
+            const C* g = lo + (size_t)comp * 2 * row_w;
+            s_src[tid][0][0] = g + row_off;
+            s_src[tid][0][1] = (row_off > 0) ? g : g + (wt - 2);
+            s_src[tid][0][2] = (row_off > 0) ? g + row_off + wt : g;
+            g = hi + (size_t)comp * 2 * row_w;
+            s_src[tid][2][0] = g + row_off;
+            s_src[tid][2][1] = (row_off > 0) ? g : g + (wt - 2);
+            s_src[tid][2][2] = (row_off > 0) ? g + row_off + wt : g;
+        } else {
+            s_src[tid][0][0] = tile + (size_t)(wx - 2) * wt;
+            s_src[tid][0][1] = colg ? cl + (size_t)(wx - 2) * 2 : tile + (size_t)(wx - 2) * wt + (wt - 2);
+            s_src[tid][0][2] = colg ? ch + (size_t)(wx - 2) * 2 : tile + (size_t)(wx - 2) * wt;
+            s_src[tid][2][0] = tile;
+            s_src[tid][2][1] = colg ? cl : tile + (wt - 2);
+            s_src[tid][2][2] = colg ? ch : tile;
+        }
+    }
+    if (tid == 0) {
+        const int side_tile = tg ? 2 : wt;
+        s_stride[1][0] = wt;
+        s_stride[1][1] = side_tile;
+        for (int reg = 0; reg < 3; reg += 2) {
+            s_stride[reg][0] = split ? row_w : wt;
+            s_stride[reg][1] = split ? row_w : side_tile;
+        }
     }
     if (tid == 0) {
 #pragma unroll
@@ -176,7 +217,10 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_tma(const FusedArgsT<cplx> a) 
         const bool wanted = my_kind < 2 || (!first && (my_kind == 2 || (j >= xa && j < xb)));
         const int reg = (j < 0) ? 0 : (j >= wx ? 2 : 1);
         const int rel = (j < 0) ? j + 2 : (j >= wx ? j - wx : j);
-        const C* src = s_src[my_arr][reg] + (size_t)rel * wt;
+        const C* const* tab = s_src[my_arr][reg];
+        const int st_main = s_stride[reg][0];
+        const int st_side = (my_kind == 3) ? st_main : s_stride[reg][1];     // x has no ghost columns: its halo is never used
+        const C* src = tab[0] + (size_t)rel * st_main;
         const unsigned int bar = bar0 + 8u * slot, dst = my_dst + stage_bytes * slot;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
                      "r"(wanted ? (unsigned int)(ncols * (int)sizeof(C)) : 0u)
@@ -184,8 +228,10 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_tma(const FusedArgsT<cplx> a) 
         if (wanted) {
             bulk_g2s_u32(dst + (unsigned int)((m_lo - c_lo) * (int)sizeof(C)), src + m_lo,
                          (unsigned int)((m_hi - m_lo) * (int)sizeof(C)), bar);
-            if (n_left) bulk_g2s_u32(dst, src + (wt + c_lo), (unsigned int)(n_left * (int)sizeof(C)), bar);
-            if (n_right) bulk_g2s_u32(dst + (unsigned int)((wt - c_lo) * (int)sizeof(C)), src, (unsigned int)(n_right * (int)sizeof(C)), bar);
+            if (n_left) bulk_g2s_u32(dst, tab[1] + (size_t)rel * st_side, (unsigned int)(n_left * (int)sizeof(C)), bar);
+            if (n_right)
+                bulk_g2s_u32(dst + (unsigned int)((wt - c_lo) * (int)sizeof(C)), tab[2] + (size_t)rel * st_side,
+                             (unsigned int)(n_right * (int)sizeof(C)), bar);
         }
     };
 
@@ -199,7 +245,9 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_tma(const FusedArgsT<cplx> a) 
     for (int q = 0; q < 2; q++) Tr[q][0] = Tr[q][1] = HX[q] = zero;
     double acc[2] = {0.0, 0.0};
     const R mass = (R)a.mass;
-    const R h0 = (R)(-0.5 * ((t == wt - 1) ? a.sR_edge : 1.0)), h1 = (R)(-0.5);
+    // the time link of column -1 (a ghost column, or the wrapped column wt-1) carries the sign of the -t hop into column 0,
+    // that of column wt-1 the sign of the +t hop out of it; on a tile that is whole in t both are the same link
+    const R h0 = (R)(-0.5 * ((tc == -1) ? a.sL_edge : ((t == wt - 1) ? a.sR_edge : 1.0))), h1 = (R)(-0.5);
 
 #pragma unroll
     for (int q = 0; q < STAGES - 1; q++) issue_row(j_first + q, q);
@@ -249,11 +297,26 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_tma(const FusedArgsT<cplx> a) 
                     a.d_new[n] = p0;
                     a.d_new[V + n] = p1;
                 } else if (split && j < 0) {             // keep d_k's ghost rows for the next iteration
-                    a.gd_lo[(j + 2) * wt + t] = p0;
-                    a.gd_lo[2 * wt + (j + 2) * wt + t] = p1;
+                    a.gd_lo[(j + 2) * row_w + row_off + t] = p0;
+                    a.gd_lo[2 * row_w + (j + 2) * row_w + row_off + t] = p1;
                 } else if (split && j >= wx) {
-                    a.gd_hi[(j - wx) * wt + t] = p0;
-                    a.gd_hi[2 * wt + (j - wx) * wt + t] = p1;
+                    a.gd_hi[(j - wx) * row_w + row_off + t] = p0;
+                    a.gd_hi[2 * row_w + (j - wx) * row_w + row_off + t] = p1;
+                }
+            } else if (MODE == FUSED_CG && tg && col_active && (tc < 0 || tc >= wt)) {
+                // a halo column of the TILE (edge strips of a lattice split along t): d_k's ghost columns, and in the
+                // ghost rows of a 2-D split the corner entries
+                const int ci = (tc < 0) ? tc + 2 : tc - wt;
+                if (j >= xa && j < xb) {
+                    C* g = (tc < 0) ? a.tgd_lo : a.tgd_hi;
+                    g[j * 2 + ci] = p0;
+                    g[2 * wx + j * 2 + ci] = p1;
+                } else if (split && row_off > 0 && (j < 0 || j >= wx)) {
+                    C* g = (j < 0) ? a.gd_lo : a.gd_hi;
+                    const int rr_ = (j < 0) ? j + 2 : j - wx;
+                    const int cc = (tc < 0) ? tc + 2 : row_off + tc;
+                    g[rr_ * row_w + cc] = p0;
+                    g[2 * row_w + rr_ * row_w + cc] = p1;
                 }
             }
             P[c][0] = p0;

@@ -157,6 +157,7 @@ static int dev_kinetic(sm_ctx* c, const double* pi, double* d_out1) {
 }
 
 static int dev_leap_update(sm_ctx* c, cplx* U, double* pi, const double* F, double eps_pi, double eps_u) {
+    NvtxRange nvtx("sm:leapfrog update");
     k_leap_update<<<c->flat_blocks_c, kBlock, 0, c->stream>>>(U, pi, F, eps_pi, eps_u, 2 * c->V);
     KCHECK();
     c->launches++;
@@ -323,6 +324,7 @@ static int hmc_force_eo(sm_ctx* c, const cplx* U, const cplx* phi, double* F, Tr
 }
 
 static int hmc_force(sm_ctx* c, const cplx* U, const cplx* phi, double* F, TrajAcc* acc) {
+    NvtxRange nvtx("sm:HMC::Force");
     if (c->solver == SM_SOLVER_EVENODD) return hmc_force_eo(c, U, phi, F, acc);
     int ok = 0, its = 0;
     const cplx* x0 = nullptr;
@@ -375,6 +377,7 @@ static int hmc_adopt_phi(sm_ctx* c) {
 
 // HMC::Leapfrog (hmc.cpp:63-103): position first, MD_steps-1 force evaluations
 static int hmc_leapfrog(sm_ctx* c, TrajAcc* acc) {
+    NvtxRange nvtx("sm:HMC::Leapfrog");
     const int md = c->hp.md_steps;
     const double eps = c->hp.trajectory_length / (md * 1.0);
     CU(cudaMemcpyAsync(c->pip, c->pi, sizeof(double) * 2 * c->V, cudaMemcpyDeviceToDevice, c->stream));
@@ -393,6 +396,7 @@ static int hmc_leapfrog(sm_ctx* c, TrajAcc* acc) {
 // HMC::Hamiltonian (hmc.cpp:135-149) = sum 1/2 pi^2 + [ beta sum Re(1-P) + Re dot((DD^dagger)^-1 phi, phi) ]
 // device sums land in c->sums[base .. base+5): kinetic, sum Re P, gauge action, Re dot, Im dot
 static int hmc_hamiltonian_async(sm_ctx* c, const cplx* U, const double* pi, const cplx* phi, int base, TrajAcc* acc) {
+    NvtxRange nvtx("sm:HMC::Hamiltonian");
     TRY(dev_kinetic(c, pi, c->sums + base));
     TRY(dev_plaquette(c, U, c->hp.beta, nullptr, c->sums + base + 1));
     int ok = 0, its = 0;

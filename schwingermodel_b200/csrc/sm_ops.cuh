@@ -199,14 +199,99 @@ static int exchange_rows2(sm_ctx* c, const cplx* field, cplx* lo_dst, cplx* hi_d
     return SM_OK;
 }
 
-// one-pass D D^dagger (sm_fused.cuh): a single tile, or tiles split along x only (ranks_t == 1,
-// 2-row ghosts); a split along t keeps the two-pass kernels.  C = cplx (double) everywhere except in the
+// One-pass D D^dagger on a lattice split along t (and possibly x): 2-deep ghost columns from packed strips, ghost rows
+// widened by the corner entries, everything exchanged by NCCL on the compute stream before ONE launch of k_dd_tma (no
+// interior/boundary overlap yet).  CG: only r travels; the ghost columns / rows / corners of d_k are written by the pass.
+template <int MODE>
+static int launch_fused_tsplit(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, double m0, double* sums_out, const cplx* r,
+                               cplx* x, cplx* d_new, int k) {
+    TRY(tg_alloc(c));
+    FusedArgsT<cplx> a{};
+    a.U = U;
+    a.in = in;
+    a.out = out;
+    a.wx = c->wx;
+    a.wt = c->wt;
+    a.V = c->V;
+    a.rows_per_block = c->fus_rows;
+    a.cols_per_strip = c->fus_cols;
+    a.mass = m0 + 2;
+    a.sR_edge = c->sR_edge();
+    a.sL_edge = c->sL_edge();
+    a.partials = c->partials;
+    a.ticket = c->tickets + TK_WILSON;
+    a.sums_out = sums_out;
+    a.st = c->cg;
+    a.r = r;
+    a.x = x;
+    a.d_new = d_new;
+    a.first = (k == 0);
+    a.cur = k & 1;
+    a.nchunks = c->fus_grid.y;
+    a.chunk_mode = 0;
+    a.tg_on = 1;
+    a.row_w = c->wt + 4;
+    const bool rows = tg_rows(c);
+    if (c->tg_U_valid_for != U) {
+        TRY(tg_exchange(c, U, 0, c->stream));
+        c->tg_U_valid_for = U;
+    }
+    const int mv = (MODE == FUSED_CG) ? 2 : 1;
+    TRY(tg_exchange(c, (MODE == FUSED_CG) ? r : in, mv, c->stream));
+    a.tgU_lo = c->tg_col[0][0];
+    a.tgU_hi = c->tg_col[0][1];
+    if (rows) {
+        a.gU_lo = c->tg_row[0][0];
+        a.gU_hi = c->tg_row[0][1];
+    }
+    if (MODE == FUSED_CG) {
+        const int cur = k & 1, dk = 3 + cur, dp = 3 + (cur ^ 1);
+        a.tgr_lo = c->tg_col[2][0];
+        a.tgr_hi = c->tg_col[2][1];
+        a.tgin_lo = c->tg_col[dp][0];
+        a.tgin_hi = c->tg_col[dp][1];
+        a.tgd_lo = c->tg_col[dk][0];
+        a.tgd_hi = c->tg_col[dk][1];
+        if (rows) {
+            a.gr_lo = c->tg_row[2][0];
+            a.gr_hi = c->tg_row[2][1];
+            a.gin_lo = c->tg_row[dp][0];
+            a.gin_hi = c->tg_row[dp][1];
+            a.gd_lo = c->tg_row[dk][0];
+            a.gd_hi = c->tg_row[dk][1];
+        }
+    } else {
+        a.tgin_lo = c->tg_col[1][0];
+        a.tgin_hi = c->tg_col[1][1];
+        if (rows) {
+            a.gin_lo = c->tg_row[1][0];
+            a.gin_hi = c->tg_row[1][1];
+        }
+    }
+    constexpr int STAGES = (MODE == FUSED_CG) ? 2 : 4;
+    const size_t smem = fused_tma_smem_bytes(MODE, STAGES, c->fus_block.x);
+    const unsigned int attr_bit = 1u << (24 + MODE);
+    if (!(c->attr_done & attr_bit)) {
+        CU(cudaFuncSetAttribute(k_dd_tma<MODE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        c->attr_done |= attr_bit;
+    }
+    k_dd_tma<MODE, STAGES><<<c->fus_grid, c->fus_block, smem, c->stream>>>(a);
+    KCHECK();
+    c->launches++;
+    return SM_OK;
+}
+
+// one-pass D D^dagger (sm_fused.cuh, sm_fused_tma.cuh): a single tile, tiles split along x only (ranks_t == 1, 2-row
+// ghosts, peer-memory halos), or -- k_dd_tma only -- tiles split along t as well (launch_fused_tsplit).  C = cplx (double) everywhere except in the
 // inner solve of the opt-in mixed-precision CG (C = cplxf, single tile only).
 template <typename C, int MODE>
 static int launch_fused(sm_ctx* c, const C* U, const C* in, C* out, double m0, double* sums_out = nullptr,
                         const C* r = nullptr, C* x = nullptr, C* d_new = nullptr, int k = 0) {
     constexpr bool kDouble = std::is_same<C, cplx>::value;
     if (!kDouble && c->dist()) return fail(SM_ERR_STATE, "single-precision passes run on a single tile only");
+    if constexpr (kDouble) {
+        if (tg_cols(c)) return launch_fused_tsplit<MODE>(c, U, in, out, m0, sums_out, r, x, d_new, k);
+    }
     FusedArgsT<C> a{};
     a.U = U;
     a.in = in;
@@ -330,7 +415,12 @@ static int launch_fused(sm_ctx* c, const C* U, const C* in, C* out, double m0, d
     return SM_OK;
 }
 
-static bool fused_ok(const sm_ctx* c) { return c->use_fused && (!c->dist() || (c->rt == 1 && c->wx >= 4)); }
+static bool fused_ok(const sm_ctx* c) {
+    if (!c->use_fused) return false;
+    if (!c->dist()) return !(c->self_t || c->self_x) || (c->fused_tma && c->wx >= 4 && c->wt >= 4);
+    if (c->rt == 1) return c->wx >= 4;
+    return c->tsplit_onepass && c->fused_tma && c->wx >= 4 && c->wt >= 4;     // ghost columns: k_dd_tma only
+}
 
 // D D^dagger: one pass over HBM on a single tile, else D^dagger then D through the context's
 // scratch field (the reference's global DTEMP, dirac_operator.cpp:477-480)

@@ -831,3 +831,32 @@ def test_evenodd_hmc_force_reversibility_and_chain(sb):
         apps[solver] = r.dd_applications
     assert apps["evenodd"] < 0.5 * apps["reference"], apps
     lat.close()
+
+
+@pytest.mark.parametrize("ghosts", ["t", "xt"])
+def test_one_pass_with_ghost_columns_on_one_tile(sb, ghosts):
+    """The one-pass D D^dagger of lattices split along t (2-deep ghost columns from packed strips, ghost rows widened by
+    the corner entries, d's ghosts written by the CG pass) exercised on ONE GPU: SM_SELF_GHOSTS makes a single tile take
+    its own opposite edges as ghosts through the same pack kernels, buffers and kernel paths a split lattice uses (only
+    the NCCL send/recv is replaced by a device copy).  Against the oracle and against the plain single-tile path, on
+    ragged shapes, incl. CG stopped mid-way (the ghost columns of d_k are rebuilt every iteration)."""
+    from oracle.port import Port, gaussian_fields
+    for nx, nt, m0 in [(64, 48, -0.05), (37, 300, 0.02), (300, 37, 0.0), (256, 256, 0.0), (130, 70, 0.1), (8, 8, 0.2)]:
+        P = Port(nx, nt)
+        U = P.hot_start(77)
+        phi, _ = gaussian_fields(nx, nt, 78)
+        os.environ.update(SM_SELF_GHOSTS=ghosts, SM_CLUSTER_CG="0", SM_DD_PATH="onepass")
+        lat = sb.Lattice(nx, nt)
+        for k in ("SM_SELF_GHOSTS", "SM_CLUSTER_CG", "SM_DD_PATH"):
+            os.environ.pop(k)
+        assert lat.one_pass_dd()
+        want = P.DDdag(U, phi, m0)
+        assert relerr(lat.D_D_dagger_phi(U, phi, m0), want) <= TOL_D, (nx, nt)
+        xo, oko, apps, _ = P.cg(U, phi, m0)
+        x, ok, its = lat.conjugate_gradient(U, phi, m0)
+        assert ok == oko == 1 and abs(its + 2 - apps) <= 1, (nx, nt, its, apps)
+        assert relerr(x, xo) <= TOL_X, (nx, nt)
+        lat.set_cg(1e-10, 9)
+        xm, okm, itm = lat.conjugate_gradient(U, phi, m0)
+        assert okm == 0 and itm == 9 and relerr(xm, P.cg(U, phi, m0, 1e-10, 9)[0]) <= 1e-10, (nx, nt)
+        lat.close()
