@@ -69,6 +69,12 @@ struct FusedArgsT {
     // -2 (they carry the corner entries of a 2-D split); without, row_w = wt.  tg_on == 0: wrap in t inside the tile.
     int tg_on;
     int row_w;
+    // which strips a launch covers (k_dd_tma; 0 everywhere else): 0 all (strip = blockIdx.x), 1 the interior strips
+    // 1 .. nstrips-2, 2 the two edge strips -- the only ones that read ghost columns; they follow the halo exchange on the
+    // comm stream while the interior strips compute.  A pass made of several launches numbers its partial sums explicitly:
+    // part_total > 0: this launch's blocks are part_base + (blockIdx.y * gridDim.x + blockIdx.x) of part_total.
+    int strip_mode, nstrips;
+    int part_base, part_total;
     const C* tgU_lo;
     const C* tgU_hi;
     const C* tgin_lo;  // psi (PLAIN/DOT) or d_{k-1} (CG)

@@ -99,12 +99,16 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_tma(const FusedArgsT<cplx> a) 
     C alpha = mkc<C>(0, 0);
     bool first = true;
     if (MODE == FUSED_CG) {
-        if (!fused_cg_begin(a, blockIdx.x == 0 && blockIdx.y == 0 && tid == 0 && a.chunk_mode != 1, beta, alpha, first)) return;
+        // one lead thread per pass: in the launch that holds chunk 0 of strip 0
+        const bool lead = blockIdx.x == 0 && blockIdx.y == 0 && tid == 0 && a.chunk_mode != 1 && a.strip_mode != 1;
+        if (!fused_cg_begin(a, lead, beta, alpha, first)) return;
         fused_cg_wait_ghosts(a);      // peer-memory halos: r_k's ghost rows have arrived (before any copy reads them)
     }
 
     // columns of this block: the strip + 2 halo columns each side, c_lo <= tc < c_lo + ncols (unwrapped)
-    const int c_lo = blockIdx.x * a.cols_per_strip - 2;
+    const int strip = (a.strip_mode == 1) ? (int)blockIdx.x + 1
+                                          : (a.strip_mode == 2 ? (blockIdx.x == 0 ? 0 : a.nstrips - 1) : (int)blockIdx.x);
+    const int c_lo = strip * a.cols_per_strip - 2;
     const int ncols = min(a.cols_per_strip + 4, wt + 2 - c_lo);
     const int tc = c_lo + tid;
     const int t = wrap_idx(tc, wt);
@@ -360,7 +364,9 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_tma(const FusedArgsT<cplx> a) 
     }
 
     if (MODE != FUSED_PLAIN) {
-        if (grid_reduce<2>(acc, a.partials, a.ticket, (int)gridDim.x * a.nchunks, chunk * (int)gridDim.x + (int)blockIdx.x)) {
+        const int nparts = a.part_total > 0 ? a.part_total : (int)gridDim.x * a.nchunks;
+        const int part = a.part_total > 0 ? a.part_base + (int)(blockIdx.y * gridDim.x + blockIdx.x) : chunk * (int)gridDim.x + (int)blockIdx.x;
+        if (grid_reduce<2>(acc, a.partials, a.ticket, nparts, part)) {
             if (tid < 32) fused_sums_out(a, acc);
         }
     }

@@ -203,10 +203,9 @@ static int exchange_rows2(sm_ctx* c, const cplx* field, cplx* lo_dst, cplx* hi_d
 // widened by the corner entries, everything exchanged by NCCL on the compute stream before ONE launch of k_dd_tma (no
 // interior/boundary overlap yet).  CG: only r travels; the ghost columns / rows / corners of d_k are written by the pass.
 template <int MODE>
-static int launch_fused_tsplit(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, double m0, double* sums_out, const cplx* r,
-                               cplx* x, cplx* d_new, int k) {
-    TRY(tg_alloc(c));
-    FusedArgsT<cplx> a{};
+static int fused_tsplit_args(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, double m0, double* sums_out, const cplx* r,
+                             cplx* x, cplx* d_new, int k, FusedArgsT<cplx>& a) {
+    a = FusedArgsT<cplx>{};
     a.U = U;
     a.in = in;
     a.out = out;
@@ -232,12 +231,6 @@ static int launch_fused_tsplit(sm_ctx* c, const cplx* U, const cplx* in, cplx* o
     a.tg_on = 1;
     a.row_w = c->wt + 4;
     const bool rows = tg_rows(c);
-    if (c->tg_U_valid_for != U) {
-        TRY(tg_exchange(c, U, 0, c->stream));
-        c->tg_U_valid_for = U;
-    }
-    const int mv = (MODE == FUSED_CG) ? 2 : 1;
-    TRY(tg_exchange(c, (MODE == FUSED_CG) ? r : in, mv, c->stream));
     a.tgU_lo = c->tg_col[0][0];
     a.tgU_hi = c->tg_col[0][1];
     if (rows) {
@@ -275,9 +268,76 @@ static int launch_fused_tsplit(sm_ctx* c, const cplx* U, const cplx* in, cplx* o
         CU(cudaFuncSetAttribute(k_dd_tma<MODE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         c->attr_done |= attr_bit;
     }
-    k_dd_tma<MODE, STAGES><<<c->fus_grid, c->fus_block, smem, c->stream>>>(a);
+    a.nstrips = (int)c->fus_grid.x;
+    return SM_OK;
+}
+
+template <int MODE>
+static int launch_fused_tsplit(sm_ctx* c, const cplx* U, const cplx* in, cplx* out, double m0, double* sums_out, const cplx* r,
+                               cplx* x, cplx* d_new, int k) {
+    TRY(tg_alloc(c));
+    constexpr int STAGES = (MODE == FUSED_CG) ? 2 : 4;
+    const size_t smem = fused_tma_smem_bytes(MODE, STAGES, c->fus_block.x);
+    const int S = (int)c->fus_grid.x;
+    const bool rows = tg_rows(c);
+    const cplx* moving = (MODE == FUSED_CG) ? r : in;
+    const int mv = (MODE == FUSED_CG) ? 2 : 1;
+    if (c->tg_U_valid_for != U) {
+        TRY(tg_exchange(c, U, 0, c->stream));
+        c->tg_U_valid_for = U;
+    }
+    FusedArgsT<cplx> a{};
+    // Overlap: only the two edge strips read ghost columns and only the boundary bands read ghost rows.  They follow the
+    // exchange on the comm stream; the interior strips (interior rows) run meanwhile on the compute stream.
+    const bool overlap = c->overlap && S >= 3 && (!rows || c->fus_split_chunks >= 1);
+    if (!overlap) {
+        TRY(tg_exchange(c, moving, mv, c->stream));
+        TRY((fused_tsplit_args<MODE>(c, U, in, out, m0, sums_out, r, x, d_new, k, a)));
+        k_dd_tma<MODE, STAGES><<<c->fus_grid, c->fus_block, smem, c->stream>>>(a);
+        KCHECK();
+        c->launches++;
+        return SM_OK;
+    }
+    CU(cudaEventRecord(c->ev_ready, c->stream));
+    CU(cudaStreamWaitEvent(c->comm_stream, c->ev_ready, 0));
+    TRY(tg_exchange(c, moving, mv, c->comm_stream));
+    TRY((fused_tsplit_args<MODE>(c, U, in, out, m0, sums_out, r, x, d_new, k, a)));
+    const int edge_chunks = (int)c->fus_grid.y;                                   // edge strips: uniform chunks over all rows
+    const int int_chunks = rows ? c->fus_split_chunks : (int)c->fus_grid.y;       // interior strips
+    const int n_edge = 2 * edge_chunks, n_int = (S - 2) * int_chunks, n_band = rows ? (S - 2) * 2 : 0;
+    a.part_total = n_edge + n_int + n_band;
+    // edge strips (all rows), then the two boundary bands of the interior strips: comm stream, behind the exchange
+    a.strip_mode = 2;
+    a.chunk_mode = 0;
+    a.part_base = 0;
+    k_dd_tma<MODE, STAGES><<<dim3(2, edge_chunks, 1), c->fus_block, smem, c->comm_stream>>>(a);
     KCHECK();
     c->launches++;
+    if (rows) {
+        a.strip_mode = 1;
+        a.chunk_mode = 2;
+        a.rb = c->fus_rb;
+        a.part_base = n_edge + n_int;
+        k_dd_tma<MODE, STAGES><<<dim3(S - 2, 2, 1), c->fus_block, smem, c->comm_stream>>>(a);
+        KCHECK();
+        c->launches++;
+    }
+    CU(cudaEventRecord(c->ev_ghost, c->comm_stream));
+    // interior strips, interior rows: compute stream, no ghosts
+    a.strip_mode = 1;
+    a.part_base = n_edge;
+    if (rows) {
+        a.chunk_mode = 1;
+        a.rb = c->fus_rb;
+        a.rows_per_block = c->fus_split_rows;
+    } else {
+        a.chunk_mode = 0;
+        a.rows_per_block = c->fus_rows;
+    }
+    k_dd_tma<MODE, STAGES><<<dim3(S - 2, int_chunks, 1), c->fus_block, smem, c->stream>>>(a);
+    KCHECK();
+    c->launches++;
+    CU(cudaStreamWaitEvent(c->stream, c->ev_ghost, 0));
     return SM_OK;
 }
 

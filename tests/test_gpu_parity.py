@@ -841,7 +841,10 @@ def test_one_pass_with_ghost_columns_on_one_tile(sb, ghosts):
     the NCCL send/recv is replaced by a device copy).  Against the oracle and against the plain single-tile path, on
     ragged shapes, incl. CG stopped mid-way (the ghost columns of d_k are rebuilt every iteration)."""
     from oracle.port import Port, gaussian_fields
-    for nx, nt, m0 in [(64, 48, -0.05), (37, 300, 0.02), (300, 37, 0.0), (256, 256, 0.0), (130, 70, 0.1), (8, 8, 0.2)]:
+    # (tiles with >= 3 strips take the overlapped form: edge strips and boundary bands behind the exchange on the comm stream,
+    # interior strips on the compute stream, one reduction over the three launches)
+    for nx, nt, m0 in [(64, 48, -0.05), (37, 300, 0.02), (300, 37, 0.0), (256, 256, 0.0), (130, 70, 0.1), (8, 8, 0.2),
+                       (64, 1000, 0.0), (300, 600, -0.03)]:
         P = Port(nx, nt)
         U = P.hot_start(77)
         phi, _ = gaussian_fields(nx, nt, 78)
