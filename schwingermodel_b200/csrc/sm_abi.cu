@@ -8,7 +8,8 @@
 // ================================================================================================
 // ---- peer-memory windows (halo rows and CG sums over NVLink) -----------------------------------------
 static int p2p_make_window(sm_ctx* c, cudaIpcMemHandle_t* h) {
-    if (!c->dist() || c->rt != 1 || c->wx < 4) return fail(SM_ERR_STATE, "peer-memory halos need a lattice split along x only");
+    if (!c->dist() || (c->rt != 1 && c->rx != 1) || c->wx < 4 || c->wt < 4)
+        return fail(SM_ERR_STATE, "peer-memory halos need a lattice split along one axis only");
     if (!c->win) {
         c->win_bytes = win_total_bytes(c);
         CU(cudaMalloc((void**)&c->win, c->win_bytes));
@@ -29,7 +30,9 @@ static int p2p_open_windows(sm_ctx* c, const void* all_handles) {
     if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qr) != cudaSuccess || fn == nullptr)
         return fail(SM_ERR_CUDA, "cuStreamWaitValue32 is not available");
     c->wait_value32 = (CUresult(*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int))fn;
-    const bool all = c->nranks <= kMaxPeers;
+    const bool along_t = c->rt > 1;                      // split along t: neighbours -t / +t, halos only (sums stay with NCCL)
+    const int nb_lo = along_t ? c->nb_tm : c->nb_xm, nb_hi = along_t ? c->nb_tp : c->nb_xp;
+    const bool all = c->nranks <= kMaxPeers && !along_t;
     std::vector<void*> opened(c->nranks, nullptr);
     opened[c->rank] = c->win;
     auto open_rank = [&](int r) -> int {
@@ -41,15 +44,15 @@ static int p2p_open_windows(sm_ctx* c, const void* all_handles) {
     };
     int rc = SM_OK;
     for (int r = 0; r < c->nranks && rc == SM_OK; r++)
-        if (all || r == c->nb_xm || r == c->nb_xp) rc = open_rank(r);
+        if (all || r == nb_lo || r == nb_hi) rc = open_rank(r);
     if (rc != SM_OK) {
         for (int r = 0; r < c->nranks; r++)
             if (opened[r] && r != c->rank) cudaIpcCloseMemHandle(opened[r]);
         cudaGetLastError();
         return rc;
     }
-    c->peer_win[0] = opened[c->nb_xm];
-    c->peer_win[1] = opened[c->nb_xp];
+    c->peer_win[0] = opened[nb_lo];
+    c->peer_win[1] = opened[nb_hi];
     if (all)
         for (int r = 0; r < c->nranks; r++) c->peer_all[r] = opened[r];
     c->p2p = true;
@@ -61,7 +64,8 @@ static int p2p_open_windows(sm_ctx* c, const void* all_handles) {
 // by ncclAllGather, every rank maps its peers.  All ranks then agree (ncclAllReduce of a flag) on whether the windows
 // are usable -- ranks in one process, or GPUs without peer access, fall back to NCCL send/recv + all-reduce together.
 static int p2p_auto_connect(sm_ctx* c) {
-    if (c->rt != 1 || c->wx < 4) return SM_OK;
+    if ((c->rt != 1 && c->rx != 1) || c->wx < 4 || c->wt < 4) return SM_OK;
+    if (c->rt > 1 && !(c->tsplit_onepass && c->fused_tma)) return SM_OK;
     if (const char* e = getenv("SM_P2P"))
         if (atoi(e) == 0) return SM_OK;
     cudaIpcMemHandle_t h;
@@ -277,6 +281,7 @@ int sm_destroy(sm_ctx* c) {
     cudaEventDestroy(c->ev_t0);
     cudaEventDestroy(c->ev_t1);
     cudaEventDestroy(c->ev_ghost);
+    cudaEventDestroy(c->ev_packed);
     delete c;
     return SM_OK;
 }

@@ -117,7 +117,7 @@ struct sm_ctx {
     int device = 0, sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t comm_stream = nullptr;   // halo exchanges that overlap the interior blocks
-    cudaEvent_t ev_ready = nullptr, ev_ghost = nullptr;
+    cudaEvent_t ev_ready = nullptr, ev_ghost = nullptr, ev_packed = nullptr;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;   // trajectory timing
     bool overlap = true;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_poll[2] = {nullptr, nullptr};
@@ -272,6 +272,7 @@ static int ctx_common_init(sm_ctx* c) {
     CU(cudaEventCreate(&c->ev_t0));
     CU(cudaEventCreate(&c->ev_t1));
     CU(cudaEventCreateWithFlags(&c->ev_ghost, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming));
     if (const char* e = getenv("SM_OVERLAP")) c->overlap = atoi(e) != 0;
     if (const char* e = getenv("SM_GRAPHS")) c->use_graphs = atoi(e) != 0;
     if (const char* e = getenv("SM_FUSED_TMA")) c->fused_tma = atoi(e) != 0;

@@ -118,12 +118,14 @@ static int tg_alloc(sm_ctx* c) {
 
 // field -> ghost columns and (widened) ghost rows of `kind`: t direction first, then x including the fresh ghost columns,
 // so the corner entries arrive without diagonal messages (the reference sends them separately, gauge_conf.cpp:225-227)
-static int tg_exchange(sm_ctx* c, const cplx* f, int kind, cudaStream_t st) {
+// `packed` (may be null): recorded on `st` right after the column pack, i.e. immediately before the first NCCL kernel.
+static int tg_exchange(sm_ctx* c, const cplx* f, int kind, cudaStream_t st, cudaEvent_t packed = nullptr) {
     const size_t nc = tg_col_elems(c), nr = tg_row_elems(c);
     cplx *slo = c->tg_sendc, *shi = c->tg_sendc + nc;
     k_pack_cols2<<<(int)((nc + kBlock - 1) / kBlock), kBlock, 0, st>>>(f, c->wx, c->wt, c->V, slo, shi);
     KCHECK();
     c->launches++;
+    if (packed != nullptr) CU(cudaEventRecord(packed, st));
     if (c->rt > 1) {
         NC(g_nccl.GroupStart());
         NC(g_nccl.Send(slo, 2 * nc, ncclDouble, c->nb_tm, c->comm, st));      // my first columns  -> their "hi"

@@ -593,4 +593,31 @@ __global__ void __launch_bounds__(kBlock) k_push_rows(const cplx* __restrict__ f
     }
 }
 
+// The same for a lattice split along t: columns 0,1 -> the -t neighbour's "hi" ghost columns, columns wt-2, wt-1 -> the +t
+// neighbour's "lo"; ghost layout [component][wx rows][2] (what k_pack_cols2 + send/recv deliver on the NCCL path).
+__global__ void __launch_bounds__(kBlock) k_push_cols(const cplx* __restrict__ field, int wx, int wt, int V,
+                                                      cplx* __restrict__ peer_tm_hi, cplx* __restrict__ peer_tp_lo,
+                                                      unsigned int* flag_tm, unsigned int* flag_tp,
+                                                      unsigned int epoch, unsigned int* ticket) {
+    const int per_side = 4 * wx;
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * per_side; i += stride) {
+        const int side = i / per_side, e = i - side * per_side;          // e = (comp, row, c)
+        const int comp = e / (2 * wx), q = e - comp * 2 * wx, row = q >> 1, cc = q & 1;
+        const cplx v = ld_stream(field + (size_t)comp * V + (size_t)row * wt + (side == 0 ? cc : wt - 2 + cc));
+        (side == 0 ? peer_tm_hi : peer_tp_lo)[e] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        if (t == gridDim.x - 1) {           // every block's columns are out: publish the epoch
+            *ticket = 0u;
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag_tm), "r"(epoch) : "memory");
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag_tp), "r"(epoch) : "memory");
+        }
+    }
+}
+
 }  // namespace sm
