@@ -345,12 +345,11 @@ static int launch_fused_tsplit(sm_ctx* c, const cplx* U, const cplx* in, cplx* o
     }
     CU(cudaEventRecord(c->ev_ready, c->stream));
     CU(cudaStreamWaitEvent(c->comm_stream, c->ev_ready, 0));
-    // The interior launch must not reach the GPU before the send/recv kernel does: its blocks take every register of every
-    // SM, and a communication kernel that becomes ready a few microseconds later (behind the pack) would wait for a whole
-    // chunk to retire (measured on 1 x 2: 0.69 ms per pass against 0.57 without any overlap).  Holding the interior back
-    // until the pack is done makes both ready at the same instant, and the comm stream has the higher priority.
-    TRY(exchange_moving(c->comm_stream, c->ev_packed));
-    CU(cudaStreamWaitEvent(c->stream, c->ev_packed, 0));
+    // Peer-memory push: the interior launch is held until the push kernel is through, so that its blocks -- which take every
+    // register of every SM -- cannot keep the push from starting (1 x 8 on 8192^2: 0.159 ms per pass).  With the two NCCL
+    // phases of a 2-D split the same gate was slower (2 x 4: 0.224 against 0.195 ms), so it is not applied there.
+    TRY(exchange_moving(c->comm_stream, push ? c->ev_packed : nullptr));
+    if (push) CU(cudaStreamWaitEvent(c->stream, c->ev_packed, 0));
     TRY((fused_tsplit_args<MODE>(c, U, in, out, m0, sums_out, r, x, d_new, k, a)));
     use_window(a);
     const int edge_chunks = (int)c->fus_grid.y;                                   // edge strips: uniform chunks over all rows
