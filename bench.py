@@ -6,12 +6,15 @@ trajectories/s (configs[2], 1024^2) reported beside it.
     python bench.py [--gpus N] [--steps K] [--warmup W]             the B200 path (libschwinger_b200.so)
     python bench.py --impl reference [...]                           the reference's CPU code on host cores
 
-One "step" is one D D^dagger application over the whole lattice (two Wilson-stencil launches).
+One "step" is one D D^dagger application over the whole lattice (one launch of the one-pass kernel per GPU; on a split
+lattice an interior and a boundary launch that run concurrently).
 `value` is site-updates/s with every field resident in HBM; `e2e` is the same unit measured
 through the reference-facing conjugate_gradient() call of the C ABI with pinned HOST buffers
 (U and phi copied in, x copied out inside the timed region): DD^dagger applications the solve
 performed x sites / wall time.  N > 1 splits the same 8192^2 lattice over ranks_x = N GPUs
-(strong scaling, the decomposition configs[3] names); launch with torchrun as the driver does.
+(strong scaling, the decomposition configs[3] names); launch with torchrun as the driver does.  Every N works on
+tiles of the same global synthetic lattice, and the line's `parity` block checks this run against the CPU oracle (seam
+bands of D D^dagger) and against the single-GPU checksums in tests/golden/bench_expect.json.
 """
 import argparse
 import json

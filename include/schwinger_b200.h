@@ -87,7 +87,8 @@ SM_API int sm_destroy(sm_ctx* ctx);
 SM_API const char* sm_last_error(void);
 /* local tile: dims[0]=width_x, dims[1]=width_t, dims[2]=rank, dims[3]=nranks */
 SM_API int sm_local_dims(const sm_ctx* ctx, int dims[4]);
-/* CG controls = the reference's mutable globals CG::tol / CG::max_iter (src/variables.cpp:35-38) */
+/* CG controls = the reference's mutable globals CG::tol / CG::max_iter (src/variables.cpp:35-38; defaults 1e-10 and 10000).
+ * max_iter <= 60000 (the iteration index shares a 32-bit epoch with the solve number on split lattices). */
 SM_API int sm_set_cg(sm_ctx* ctx, double tol, int max_iter);
 /* Solver used by every CG of the context (conjugate_gradient, HMC::Force, HMC::Action):
  *   SM_SOLVER_REFERENCE  the reference's algorithm in double precision (default; dH parity <= 1e-8)

@@ -56,7 +56,7 @@ static int p2p_open_windows(sm_ctx* c, const void* all_handles) {
     if (all)
         for (int r = 0; r < c->nranks; r++) c->peer_all[r] = opened[r];
     c->p2p = true;
-    c->peer_sums = all && c->fused_tma_or_fused_ok();
+    c->peer_sums = all && c->use_fused;     // the kernels that do their own collectives belong to the one-pass CG
     return SM_OK;
 }
 

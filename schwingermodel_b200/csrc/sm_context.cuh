@@ -228,7 +228,6 @@ struct sm_ctx {
     unsigned int* coop_bar = nullptr;
 
     bool dist() const { return nranks > 1; }
-    bool fused_tma_or_fused_ok() const { return use_fused; }
     double sR_edge() const { return (ct == rt - 1) ? -1.0 : 1.0; }
     double sL_edge() const { return (ct == 0) ? -1.0 : 1.0; }
 };
