@@ -71,10 +71,16 @@ static int p2p_auto_connect(sm_ctx* c) {
     cudaIpcMemHandle_t h;
     memset(&h, 0, sizeof(h));
     int ok = (p2p_make_window(c, &h) == SM_OK) ? 1 : 0;
-    unsigned char* d_handles = nullptr;
-    int* d_ok = nullptr;
-    CU(cudaMalloc((void**)&d_handles, (size_t)c->nranks * SM_P2P_HANDLE_BYTES));
-    CU(cudaMalloc((void**)&d_ok, sizeof(int)));
+    struct DevBuf {          // released on every return path
+        void* p = nullptr;
+        ~DevBuf() {
+            if (p) cudaFree(p);
+        }
+    } b_handles, b_ok;
+    CU(cudaMalloc(&b_handles.p, (size_t)c->nranks * SM_P2P_HANDLE_BYTES));
+    CU(cudaMalloc(&b_ok.p, sizeof(int)));
+    unsigned char* d_handles = (unsigned char*)b_handles.p;
+    int* d_ok = (int*)b_ok.p;
     CU(cudaMemcpyAsync(d_handles + (size_t)c->rank * SM_P2P_HANDLE_BYTES, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
     NC(g_nccl.AllGather(d_handles + (size_t)c->rank * SM_P2P_HANDLE_BYTES, d_handles, SM_P2P_HANDLE_BYTES, ncclChar, c->comm, c->stream));
     std::vector<unsigned char> handles((size_t)c->nranks * SM_P2P_HANDLE_BYTES);
@@ -86,8 +92,6 @@ static int p2p_auto_connect(sm_ctx* c) {
     int all_ok = 0;
     CU(cudaMemcpyAsync(&all_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    cudaFree(d_handles);
-    cudaFree(d_ok);
     if (!all_ok) {       // together or not at all
         c->p2p = false;
         c->peer_sums = false;
