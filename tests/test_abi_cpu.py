@@ -71,3 +71,37 @@ def test_file_name_tags_and_jackknife():
     rng = np.random.default_rng(0)
     d = rng.normal(size=47)
     assert abs(sb.jackknife_error(d, 20) - Port(2, 2).jackknife(d, 20)) < 1e-15
+
+
+def test_public_header_is_plain_c(tmp_path):
+    """include/schwinger_b200.h is the C ABI: it must compile as C99 (no C++-isms, no torch / CUDA types) and as C++."""
+    import subprocess
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "schwinger_b200.h"\nint main(void) { sm_traj_result r; sm_hmc_params p; (void)r; (void)p; return SM_OK; }\n')
+    inc = os.path.join(ROOT, "include")
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only"],
+                ["g++", "-std=c++17", "-Wall", "-fsyntax-only", "-x", "c++"]):
+        r = subprocess.run(cmd + ["-I", inc, str(src)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """sm_traj_result / sm_hmc_params as the ctypes mirror declares them have the size and field offsets the C compiler
+    gives the header's structs (a silent mismatch would corrupt every trajectory result)."""
+    import subprocess
+    fields = {"sm_traj_result": [f[0] for f in _abi.TrajResult._fields_], "sm_hmc_params": [f[0] for f in _abi.HmcParams._fields_]}
+    lines = ['#include <stddef.h>', '#include <stdio.h>', '#include "schwinger_b200.h"', "int main(void) {"]
+    for st, names in fields.items():
+        lines.append(f'  printf("{st} %zu", sizeof({st}));')
+        for n in names:
+            lines.append(f'  printf(" %zu", offsetof({st}, {n}));')
+        lines.append('  printf("\\n");')
+    lines += ["  return 0;", "}"]
+    src, exe = tmp_path / "layout.c", tmp_path / "layout"
+    src.write_text("\n".join(lines))
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    for line, (st, cls) in zip(out, [("sm_traj_result", _abi.TrajResult), ("sm_hmc_params", _abi.HmcParams)]):
+        got = [int(v) for v in line.split()[1:]]
+        want = [C.sizeof(cls)] + [getattr(cls, f[0]).offset for f in cls._fields_]
+        assert got == want, (st, got, want)
