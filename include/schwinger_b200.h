@@ -104,7 +104,9 @@ SM_API int sm_set_cg(sm_ctx* ctx, double tol, int max_iter);
  *                        (same determinant as D D^dagger up to a constant, hence the same gauge-field distribution);
  *                        every solve is a CG on half the sites with a ~4x smaller condition number near the critical
  *                        mass.  A different Markov chain than the reference's: dH is not comparable trajectory by
- *                        trajectory, plaquette and acceptance agree statistically.  Single tile, even Nx and Nt. */
+ *                        trajectory; plaquette agrees statistically, acceptance is higher in equilibrium.  From a hot start
+ *                        its leapfrog error is the larger one: thermalise with the reference solver (or a finer step)
+ *                        first.  Single tile, even Nx and Nt. */
 enum { SM_SOLVER_REFERENCE = 0, SM_SOLVER_MIXED = 1, SM_SOLVER_CHRONO = 2, SM_SOLVER_EVENODD = 3 };
 SM_API int sm_set_solver(sm_ctx* ctx, int solver);
 /* device time (ms) of the last sm_* call on this context, measured with CUDA events on the
