@@ -427,12 +427,18 @@ def run_b200(args):
     value = sites / (ms_per_step * 1e-3)
 
     peak, peak_src = measured_peaks()
-    # dominant kernel: one k_dd_fused pass per step (on a split lattice the pass is an interior launch plus a
+    # dominant kernel: one k_dd_tma pass per step (on a split lattice the pass is an interior launch plus a
     # boundary-band launch that run concurrently) or two k_wilson launches (lattice split along t).
     # Algorithmic bytes per launch = 96 B x sites of the tile for BOTH kernels: a Wilson-stencil pass reads psi and U
     # and writes out once (96 B per stencil site), and the one-pass D D^dagger kernel likewise reads psi and
     # U once and writes out once per D D^dagger site-update -- the intermediate D^dagger psi never reaches HBM.
     one_pass = lat.one_pass_dd()
+    # rows staged by TMA bulk copies (k_dd_tma, csrc/sm_fused_tma.cuh) unless SM_FUSED_TMA=0 selects the cp.async kernel
+    try:
+        tma = int(os.environ.get("SM_FUSED_TMA", "1")) != 0
+    except ValueError:
+        tma = False                      # the library reads the variable with atoi()
+    one_pass_kernel = "k_dd_tma" if tma else "k_dd_fused"
     passes = args.steps if one_pass else 2 * args.steps
     avg_launch_ms = ms / passes
     alg_bytes = BYTES_PER_STENCIL_SITE * V
@@ -444,7 +450,7 @@ def run_b200(args):
             traffic = json.load(f).get("k_dd_fused_bytes_per_launch" if one_pass else "k_wilson_bytes_per_launch")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
-                "kernel": "k_dd_fused (one-pass D D^dagger)" if one_pass else "k_wilson (Wilson stencil D / D^dagger)",
+                "kernel": (one_pass_kernel + " (one-pass D D^dagger)") if one_pass else "k_wilson (Wilson stencil D / D^dagger)",
                 "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_site": BYTES_PER_STENCIL_SITE,
                 "avg_launch_ms": avg_launch_ms}
     if one_pass:
