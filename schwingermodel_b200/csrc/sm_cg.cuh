@@ -103,6 +103,19 @@ static int cg_fused_loop(sm_ctx* c, const C* U, C* r, C* x, C* dbuf0, C* dbuf1, 
                 return SM_OK;
             }
         }
+        if (std::is_same<C, cplx>::value && pdl_ok(c)) {
+            CgState* st_ = st;
+            int cur_ = cur, n_ = n_elems;
+            C* r_ = r;
+            const C* Ad_ = Ad;
+            double* partials_ = c->partials;
+            unsigned int* ticket_ = c->tickets + TK_UPDATE;
+            double* sums_ = sum_target(c, &st->rr[cur ^ 1]);
+            void* params[] = {&st_, &cur_, &r_, &Ad_, &n_, &partials_, &ticket_, &sums_};
+            TRY(launch_pdl(c, (const void*)k_cg_resid<C>, dim3(c->flat_blocks_c, 1, 1), dim3(kBlock, 1, 1), 0, params));
+            c->launches++;
+            return sum_finish(c, &st->rr[cur ^ 1], 1);
+        }
         k_cg_resid<C><<<c->flat_blocks_c, kBlock, 0, c->stream>>>(st, cur, r, Ad, n_elems, c->partials,
                                                                   c->tickets + TK_UPDATE, sum_target(c, &st->rr[cur ^ 1]));
         KCHECK();

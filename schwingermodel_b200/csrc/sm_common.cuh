@@ -64,6 +64,14 @@ __device__ __forceinline__ void st_stream(cplxf* p, cplxf v) {
     asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
 }
 
+// Programmatic dependent launch (opt-in, SM_PDL=1; sm_cg.cuh): the two kernels of a one-pass CG iteration are launched
+// with cudaLaunchAttributeProgrammaticStreamSerialization, so the blocks of the next kernel may become resident -- and
+// run their prologue -- while the previous kernel drains.  `pdl_wait` returns once every grid this one depends on has
+// completed and its memory is visible: it stands before the first read of anything a predecessor wrote and before the
+// first global write.  Both are no-ops in a kernel that was launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 constexpr int kBlock = 256;          // threads per block for every kernel
 constexpr int kWarps = kBlock / 32;
 constexpr int kMaxSums = 4;          // doubles reduced per kernel (<= 2 complex numbers)

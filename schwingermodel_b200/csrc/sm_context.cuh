@@ -209,6 +209,7 @@ struct sm_ctx {
     std::vector<CgGraph> cg_graphs;
     std::vector<CgGraph> eo_graphs;   // ... and of the even-odd solver
     bool use_graphs = true;
+    bool pdl = false;             // SM_PDL=1: programmatic dependent launch of the one-pass CG kernels (single tile; sm_common.cuh)
     unsigned int attr_done = 0;   // kernel attributes already set on this context's device
     int solver = SM_SOLVER_REFERENCE;
     const cplx* cg_x0 = nullptr;      // start vector of the running solve (null: phi, as the reference)
@@ -275,6 +276,7 @@ static int ctx_common_init(sm_ctx* c) {
     if (const char* e = getenv("SM_OVERLAP")) c->overlap = atoi(e) != 0;
     if (const char* e = getenv("SM_GRAPHS")) c->use_graphs = atoi(e) != 0;
     if (const char* e = getenv("SM_FUSED_TMA")) c->fused_tma = atoi(e) != 0;
+    if (const char* e = getenv("SM_PDL")) c->pdl = atoi(e) != 0;
     if (const char* e = getenv("SM_TSPLIT_ONEPASS")) c->tsplit_onepass = atoi(e) != 0;
     if (const char* e = getenv("SM_SELF_GHOSTS")) {
         c->self_t = strchr(e, 't') != nullptr && c->nranks == 1;
@@ -400,6 +402,24 @@ static int tock(sm_ctx* c) {
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, c->ev_a, c->ev_b));
     c->last_ms = ms;
+    return SM_OK;
+}
+
+// A kernel launch that may start while its predecessor on the stream drains (programmatic dependent launch): the kernel
+// itself waits (pdl_wait, sm_common.cuh) before it touches anything the predecessor wrote.  Also valid under stream capture
+// (the edge becomes a programmatic dependency of the graph).
+static int launch_pdl(sm_ctx* c, const void* kernel, dim3 grid, dim3 block, size_t smem, void** args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CU(cudaLaunchKernelExC(&cfg, kernel, args));
     return SM_OK;
 }
 

@@ -404,6 +404,8 @@ __global__ void __launch_bounds__(kBlock) k_cg_resid(CgState* st, int cur, C* __
                                                      int n_elems, double* partials, unsigned int* ticket,
                                                      double* sums_out) {
     typedef typename RealOf<C>::type R;
+    pdl_wait();                 // (opt-in programmatic dependent launch: pass A's A d and dot(d, A d) are complete)
+    pdl_launch_dependents();
     if (st->done) return;
     const cplx alpha = cdiv(make_double2(st->rr[cur], 0.0), make_double2(st->dAd[0], st->dAd[1]));
     const C al = mkc<C>((R)alpha.x, (R)alpha.y);

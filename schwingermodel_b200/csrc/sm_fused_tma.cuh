@@ -99,6 +99,9 @@ __global__ void __launch_bounds__(kBlock, 2) k_dd_tma(const FusedArgsT<cplx> a) 
     C alpha = mkc<C>(0, 0);
     bool first = true;
     if (MODE == FUSED_CG) {
+        // (opt-in programmatic dependent launch, sm_common.cuh: nothing above this line touches global memory)
+        pdl_wait();
+        pdl_launch_dependents();
         // one lead thread per pass: in the launch that holds chunk 0 of strip 0
         const bool lead = blockIdx.x == 0 && blockIdx.y == 0 && tid == 0 && a.chunk_mode != 1 && a.strip_mode != 1;
         if (!fused_cg_begin(a, lead, beta, alpha, first)) return;

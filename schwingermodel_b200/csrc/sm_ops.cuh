@@ -391,6 +391,9 @@ static int launch_fused_tsplit(sm_ctx* c, const cplx* U, const cplx* in, cplx* o
     return SM_OK;
 }
 
+// opt-in (SM_PDL=1): the two kernels of a one-pass CG iteration on a single tile start while their predecessor drains
+static bool pdl_ok(const sm_ctx* c) { return c->pdl && !c->dist() && c->fused_tma && !c->self_t && !c->self_x; }
+
 // one-pass D D^dagger (sm_fused.cuh, sm_fused_tma.cuh): a single tile, tiles split along x only (ranks_t == 1, 2-row
 // ghosts, peer-memory halos), or -- k_dd_tma only -- tiles split along t as well (launch_fused_tsplit).  C = cplx (double) everywhere except in the
 // inner solve of the opt-in mixed-precision CG (C = cplxf, single tile only).
@@ -517,6 +520,10 @@ static int launch_fused(sm_ctx* c, const C* U, const C* in, C* out, double m0, d
         KCHECK();
         CU(cudaStreamWaitEvent(c->stream, c->ev_ghost, 0));
         c->launches += 2;
+    } else if (kDouble && MODE == FUSED_CG && pdl_ok(c)) {
+        void* params[] = {(void*)&a};
+        TRY(launch_pdl(c, (const void*)kern, c->fus_grid, c->fus_block, smem, params));
+        c->launches++;
     } else {
         kern<<<c->fus_grid, c->fus_block, smem, c->stream>>>(a);
         KCHECK();

@@ -526,9 +526,12 @@ def test_cg_execution_strategies_agree(sb):
         U = P.hot_start(5)
         phi, _ = gaussian_fields(nx, nt, 6)
         xo, oko, apps, _ = P.cg(U, phi, m0)
-        got = {}
-        for name, env in [("cluster", {}), ("graphs", {"SM_CLUSTER_CG": "0"}),
-                          ("launches", {"SM_CLUSTER_CG": "0", "SM_GRAPHS": "0"}),
+        got, full = {}, {}
+        for name, env in [("cluster", {}), ("graphs", {"SM_CLUSTER_CG": "0", "SM_PDL": "0"}),
+                          ("launches", {"SM_CLUSTER_CG": "0", "SM_GRAPHS": "0", "SM_PDL": "0"}),
+                          # programmatic dependent launch of the two kernels of an iteration: the same arithmetic
+                          ("graphs pdl", {"SM_CLUSTER_CG": "0", "SM_PDL": "1"}),
+                          ("launches pdl", {"SM_CLUSTER_CG": "0", "SM_GRAPHS": "0", "SM_PDL": "1"}),
                           ("twopass", {"SM_CLUSTER_CG": "0", "SM_DD_PATH": "twopass"})]:
             os.environ.update(env)
             lat = sb.Lattice(nx, nt)
@@ -539,6 +542,7 @@ def test_cg_execution_strategies_agree(sb):
             assert (ok, its) == (ok2, its2) and np.array_equal(x, x2), name
             assert ok == oko == 1 and abs(its + 2 - apps) <= 1, (name, its, apps)
             assert relerr(x, xo) <= TOL_X, name
+            full[name] = x
             lat.set_cg(1e-10, 11)                                      # stop mid-way: same iterate everywhere
             xm, okm, itm = lat.conjugate_gradient(U, phi, m0)
             assert okm == 0 and itm == 11
@@ -547,6 +551,8 @@ def test_cg_execution_strategies_agree(sb):
         xref = P.cg(U, phi, m0, 1e-10, 11)[0]
         for name, xm in got.items():
             assert relerr(xm, xref) <= 1e-10, name
+        assert np.array_equal(full["graphs pdl"], full["graphs"]) and np.array_equal(full["launches pdl"], full["graphs"])
+        assert np.array_equal(got["graphs pdl"], got["graphs"]) and np.array_equal(got["launches pdl"], got["graphs"])
 
 
 @pytest.mark.parametrize("nx,nt,m0", [(288, 288, 0.0), (300, 333, -0.03), (400, 401, 0.05), (512, 512, -0.1), (1100, 275, 0.0)])
