@@ -181,8 +181,8 @@ struct GridSync {
         for (int j = 0; j < NV; j++) {
             const double* part = wsum + (size_t)(slot * 2 + j) * nb;
             double p[5];
-#pragma unroll
             static_assert(kGridSyncMaxCtas == 5 * 32, "five partials per lane");
+#pragma unroll
             for (int i = 0; i < 5; i++) p[i] = (lane + 32 * i < nb) ? __ldcg(part + lane + 32 * i) : 0.0;
             double acc = ((p[0] + p[1]) + (p[2] + p[3])) + p[4];
 #pragma unroll
