@@ -378,8 +378,15 @@ int sm_tables(sm_ctx* c, int ranks_x, int ranks_t, int rank, int* RightPB, int* 
     // antiperiodic seam keyed on the rank exactly as the reference (include/dirac_operator.h:53-58)
     const double sR = ((rank + 1) % ranks_t == 0) ? -1.0 : 1.0;
     const double sL = (rank % ranks_t == 0) ? -1.0 : 1.0;
-    int *dR, *dL, *dA, *dB;
-    double *dsR, *dsL;
+    int *dR = nullptr, *dL = nullptr, *dA = nullptr, *dB = nullptr;
+    double *dsR = nullptr, *dsL = nullptr;
+    struct Release {       // the scratch tables go on every return path
+        void** p[6];
+        ~Release() {
+            for (void** q : p)
+                if (*q) cudaFree(*q);
+        }
+    } release{{(void**)&dR, (void**)&dL, (void**)&dA, (void**)&dB, (void**)&dsR, (void**)&dsL}};
     TRY(dev_alloc(&dR, (size_t)2 * m));
     TRY(dev_alloc(&dL, (size_t)2 * m));
     TRY(dev_alloc(&dA, (size_t)m));
@@ -395,9 +402,7 @@ int sm_tables(sm_ctx* c, int ranks_x, int ranks_t, int rank, int* RightPB, int* 
     CU(cudaMemcpyAsync(x1_t_1, dB, sizeof(int) * m, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(SignR, dsR, sizeof(double) * 4 * m, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(SignL, dsL, sizeof(double) * 4 * m, cudaMemcpyDeviceToHost, c->stream));
-    TRY(sync(c));
-    cudaFree(dR); cudaFree(dL); cudaFree(dA); cudaFree(dB); cudaFree(dsR); cudaFree(dsL);
-    return SM_OK;
+    return sync(c);
 }
 
 // ---- peer-memory windows: the entry points ------------------------------------------------------------
@@ -820,7 +825,7 @@ int sm_save_conf(int Nx, int Nt, const double* U0, const double* U1, const char*
             return fail(SM_ERR_IO, std::string("short write to ") + path);
         }
     }
-    fclose(f);
+    if (fclose(f) != 0) return fail(SM_ERR_IO, std::string("cannot finish writing ") + path);   // buffered data that did not fit
     return SM_OK;
 }
 

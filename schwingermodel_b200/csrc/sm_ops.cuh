@@ -281,7 +281,6 @@ static int fused_tsplit_args(sm_ctx* c, const cplx* U, const cplx* in, cplx* out
         }
     }
     constexpr int STAGES = (MODE == FUSED_CG) ? 2 : 4;
-    const size_t smem = fused_tma_smem_bytes(MODE, STAGES, c->fus_block.x);
     const unsigned int attr_bit = 1u << (24 + MODE);
     if (!(c->attr_done & attr_bit)) {
         CU(cudaFuncSetAttribute(k_dd_tma<MODE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
