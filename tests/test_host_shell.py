@@ -36,6 +36,22 @@ def test_host_shell_builds_and_fails_loudly_without_gpu(tmp_path):
     assert pos == sorted(pos)
 
 
+def test_cmake_keeps_the_reference_configure_interface(tmp_path):
+    """`cmake -DNS=.. -DNT=..` names the executable SM_${NS}x${NT} and fixes the lattice at configure time, as the reference's
+    CMakeLists.txt:17-23 does; the GPU library is a CUDA target for sm_100a only.  (Configure step only: the build itself is
+    what schwingermodel_b200/csrc/build.sh and host/Makefile do in-tree.)"""
+    import shutil
+    if shutil.which("cmake") is None:
+        pytest.skip("cmake is not installed")
+    r = subprocess.run(["cmake", "-S", ROOT, "-B", str(tmp_path), "-DNS=16", "-DNT=24"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    cache = open(os.path.join(tmp_path, "CMakeCache.txt")).read()
+    assert "NS:STRING=16" in cache and "NT:STRING=24" in cache and "CMAKE_CUDA_ARCHITECTURES" in open(
+        os.path.join(ROOT, "CMakeLists.txt")).read()
+    targets = subprocess.run(["cmake", "--build", str(tmp_path), "--target", "help"], capture_output=True, text=True).stdout
+    assert "SM_16x24" in targets and "schwinger_b200" in targets
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("nx,nt", [(8, 8), (16, 24)])
 def test_reference_cxx_interface_vs_oracle(tmp_path, nx, nt):
