@@ -33,6 +33,33 @@ def test_built_for_sm_100a_only():
     assert archs == {"sm_100a"}, out
 
 
+def test_one_pass_kernels_stage_rows_with_bulk_copies_and_nothing_uses_tensor_cores():
+    """SASS of the shipped library: every k_dd_tma instantiation stages its rows with TMA bulk copies completing on
+    mbarriers (UBLKCP + SYNCS), moves fields as 16-byte vectors, and no kernel holds a tensor-core instruction -- the
+    path has no dense contraction."""
+    import shutil
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump is not installed")
+    sass = subprocess.run(["cuobjdump", "-sass", sb.LIB_PATH], capture_output=True, text=True).stdout
+    funcs, name = {}, None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            name = line.split("Function :")[1].strip()
+            funcs[name] = []
+        elif name is not None:
+            funcs[name].append(line)
+    tma = {n: "\n".join(b) for n, b in funcs.items() if "k_dd_tma" in n}
+    assert len(tma) >= 3, sorted(funcs)          # PLAIN (3 and 4 stages), DOT, CG
+    for n, body in tma.items():
+        assert "UBLKCP" in body and "SYNCS" in body, n
+        stores = [w for line in body.splitlines() for w in line.split() if w.startswith("STG.")]
+        assert "LDS.128" in body and stores and all(w.endswith(".128") for w in stores if ".NA." in w), (n, set(stores))
+        assert "LDGSTS" not in body, n           # no per-thread cp.async left in the TMA kernels
+    everything = "\n".join("\n".join(b) for b in funcs.values())
+    for mnemonic in ("UTCMMA", "UTCHMMA", "HMMA", "DMMA", "IMMA", "QGMMA", "HGMMA"):
+        assert mnemonic not in everything, mnemonic
+
+
 def test_no_gpu_no_fallback():
     import torch
     if torch.cuda.is_available():
