@@ -230,18 +230,34 @@ def run_reference(args):
     from oracle import ref as refmod
     n = reference_lattice(args)
     U, phi = synthetic_tile("links", 1000, n, n), synthetic_tile("spinor", 2000, n, n)
+    times = None
     if refmod.available(n, n):
-        R = refmod.Ref(n, n)
-        rx, kind = reference_ranks(n), "reference"
-        cores = rx
-        reps = 1 if n >= 4096 else 2
-        times = []
-        for i in range(args.warmup + args.steps):
-            sec, count, _ = R.timed("dd", U, phi, 0.0, rx, 1, reps=reps)
-            times.append(sec / reps)
-    else:
-        # the reference did not compile here: time the C port (1 core)
+        kind = "reference"
+        for attempt in (n, 2048):          # the bench lattice itself; if this host cannot run it, the 2048^2 sample
+            try:
+                if attempt != n:
+                    n = attempt
+                    U, phi = synthetic_tile("links", 1000, n, n), synthetic_tile("spinor", 2000, n, n)
+                    if not refmod.available(n, n):
+                        break
+                R = refmod.Ref(n, n)
+                rx = cores = reference_ranks(n)
+                reps = 1 if n >= 4096 else 2
+                times = []
+                for i in range(args.warmup + args.steps):
+                    sec, count, _ = R.timed("dd", U, phi, 0.0, rx, 1, reps=reps)
+                    times.append(sec / reps)
+                break
+            except (RuntimeError, OSError, MemoryError) as e:
+                print(f"reference arm: {attempt}x{attempt} failed ({e!r})", file=sys.stderr)
+                times = None
+                if attempt == 2048:
+                    break
+    if times is None:
+        # the reference did not compile (or run) here: time the C port (1 core)
         from oracle.port import Port
+        n = min(n, 2048)
+        U, phi = synthetic_tile("links", 1000, n, n), synthetic_tile("spinor", 2000, n, n)
         P = Port(n, n)
         times = []
         for i in range(args.warmup + args.steps):
@@ -566,7 +582,16 @@ def run_b200(args):
                 line["extra"].update(extra_metrics(sb, args))
             except Exception as e:  # noqa: BLE001  -- the smaller configs must not cost the headline line
                 line["extra"]["error"] = repr(e)
-            line["cpu_baseline"] = cpu_baseline(args, U_h, phi_h)
+            try:
+                line["cpu_baseline"] = cpu_baseline(args, U_h, phi_h)
+            except Exception as e:  # noqa: BLE001  -- e.g. the host cannot fork the 8192^2 reference: take the 2048^2 sample
+                args.ref_lattice = 2048
+                try:
+                    line["cpu_baseline"] = cpu_baseline(args)
+                    line["cpu_baseline"]["note"] = f"bench lattice failed on this host ({e!r}); 2048^2 sample instead"
+                except Exception as e2:  # noqa: BLE001
+                    line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
+                                            "sample": "none", "error": repr(e2)}
     if parity is not None:
         parity["vs_single_gpu"] = compare_with_expected(parity, Lx, Lt, args)
         parity["ok"] = bool(parity["dd_seam_band_max_rel_err_vs_oracle"] <= parity["dd_tolerance"] and
