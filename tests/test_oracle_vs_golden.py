@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN, load_golden
-from oracle.port import Port
+from oracle.port import Port, gaussian_fields
 
 CASES = [(8, 8), (16, 24), (32, 32)]
 
@@ -170,3 +170,37 @@ def test_leapfrog_reversible():
     U2, p2 = P.leapfrog(U1, -p1, phi, 6, 0.5, beta, m0, tol=1e-13)
     assert np.abs(U2 - U).max() < 1e-11 and np.abs(p2 + pi).max() < 1e-10
     assert np.abs(np.abs(U1) - 1).max() < 1e-14
+
+
+def test_gauge_covariance():
+    """Under a local U(1) transformation g(n): U_mu(n) -> g(n) U_mu(n) conj(g(n + mu)), psi -> g psi the operators are
+    covariant, D[U'] (g psi) = g D[U] psi (likewise D^dagger, D D^dagger; the antiperiodic sign of the fermions in t
+    does not see g), the plaquette, the gauge action, the Hamiltonian and the force (a gauge-invariant real field) do
+    not change, and the CG solution transforms like psi -- properties of the reference's operator (eq. 34-38 of its notes)
+    that any index, sign or conjugation slip in a restatement breaks."""
+    nx, nt, m0, beta = 6, 10, -0.04, 2.0
+    P = Port(nx, nt)
+    rng = np.random.default_rng(5)
+    U = P.hot_start(77)
+    psi, _ = gaussian_fields(nx, nt, 78)
+    _, pi = gaussian_fields(nx, nt, 79)
+    g = np.exp(1j * rng.uniform(0, 2 * np.pi, (nx, nt)))
+    Ug = np.empty_like(U)
+    Ug[0] = (g * U[0].reshape(nx, nt) * np.conj(np.roll(g, -1, axis=1))).ravel()     # mu = 0: time, n + mu = (x, t+1)
+    Ug[1] = (g * U[1].reshape(nx, nt) * np.conj(np.roll(g, -1, axis=0))).ravel()     # mu = 1: space, (x+1, t)
+    gf = g.ravel()[None, :]
+    for dag in (False, True):
+        assert np.abs(P.D(Ug, gf * psi, m0, dag) - gf * P.D(U, psi, m0, dag)).max() < 1e-13
+    assert np.abs(P.DDdag(Ug, gf * psi, m0) - gf * P.DDdag(U, psi, m0)).max() < 1e-13
+    p0, p1 = P.plaquette(U, beta), P.plaquette(Ug, beta)
+    for a, b in zip(p0, p1):
+        assert np.abs(np.asarray(a) - np.asarray(b)).max() < 1e-12
+    x0, ok0, apps0, _ = P.cg(U, psi, m0, tol=1e-13)
+    x1, ok1, apps1, _ = P.cg(Ug, gf * psi, m0, tol=1e-13)
+    assert ok0 == ok1 == 1 and abs(apps0 - apps1) <= 1 and np.abs(x1 - gf * x0).max() < 1e-10 * np.abs(x0).max()
+    H0 = P.hamiltonian(U, pi, psi, beta, m0, tol=1e-13)
+    H1 = P.hamiltonian(Ug, pi, gf * psi, beta, m0, tol=1e-13)
+    assert abs(H0 - H1) < 1e-9 * abs(H0)
+    F0, _ = P.force(U, psi, beta, m0, tol=1e-13)
+    F1, _ = P.force(Ug, gf * psi, beta, m0, tol=1e-13)
+    assert np.abs(F0 - F1).max() < 1e-8 * max(1.0, np.abs(F0).max())
